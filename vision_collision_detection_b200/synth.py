@@ -1,0 +1,59 @@
+"""Deterministic synthetic dashcam clips (integer arithmetic only, so numpy on
+the host and torch on the device produce identical bytes).
+
+Two distributions: ``noise`` — i.i.d. uniform bytes, the
+worst case for antialiased-resize parity; ``dashcam`` — sky-to-road vertical
+gradient, lane/horizon block structure drifting with time, and +-16 noise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M32 = 0xFFFFFFFF
+
+
+def _hash32(idx, seed: int):
+    """32-bit integer hash evaluated in 64-bit integers (works for numpy int64
+    arrays and torch int64 tensors alike; only the low 32 bits are kept)."""
+    x = (idx * 2654435761 + (seed * 40503 + 0x9E3779B9)) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 2246822519) & _M32
+    x = x ^ (x >> 13)
+    x = (x * 3266489917) & _M32
+    x = x ^ (x >> 16)
+    return x
+
+
+def _pattern(t, y, x, c, h: int, seed: int, kind: str, lin):
+    noise = _hash32(lin, seed)
+    if kind == "noise":
+        return noise & 0xFF
+    if kind != "dashcam":
+        raise ValueError(f"unknown synthetic kind {kind!r}")
+    sky = 215 - (y * 150) // max(h, 1)
+    blocks = (((x + 3 * t) // 32 + y // 24) % 2) * 28
+    lane = ((x + y // 2 + 5 * t) % 160 < 6) * 40
+    tint = c * 9
+    v = sky + blocks + lane - tint + (noise & 31) - 16
+    return v.clip(0, 255) if hasattr(v, "clip") else v.clamp(0, 255)
+
+
+def make_clip_np(t: int, h: int, w: int, seed: int = 0, kind: str = "noise") -> np.ndarray:
+    """uint8 [T,H,W,3] on the host."""
+    tt, yy, xx, cc = np.meshgrid(np.arange(t, dtype=np.int64), np.arange(h, dtype=np.int64),
+                                 np.arange(w, dtype=np.int64), np.arange(3, dtype=np.int64), indexing="ij")
+    lin = ((tt * h + yy) * w + xx) * 3 + cc
+    return _pattern(tt, yy, xx, cc, h, seed, kind, lin).astype(np.uint8)
+
+
+def make_clip_torch(t: int, h: int, w: int, seed: int = 0, kind: str = "noise", device="cuda"):
+    """uint8 [T,H,W,3] generated on ``device`` (same bytes as make_clip_np)."""
+    import torch
+
+    ar = lambda n: torch.arange(n, dtype=torch.int64, device=device)
+    tt = ar(t).view(t, 1, 1, 1)
+    yy = ar(h).view(1, h, 1, 1)
+    xx = ar(w).view(1, 1, w, 1)
+    cc = ar(3).view(1, 1, 1, 3)
+    lin = ((tt * h + yy) * w + xx) * 3 + cc
+    return _pattern(tt, yy, xx, cc, h, seed, kind, lin).to(torch.uint8)
