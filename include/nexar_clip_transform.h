@@ -1,0 +1,157 @@
+/*
+ * nexar_clip_transform.h — C ABI of the B200 clip-transform library
+ * (libnexar_clip_b200.so).
+ *
+ * One call turns a batch of decoded uint8 dashcam clips into the normalised
+ * model-input tensor: temporal gather -> antialiased letterbox (or short-side
+ * resize + crop) -> horizontal flip -> VideoAugmentation chain -> mean/std
+ * normalise -> [B,C,T,cs,cs] (or any strided layout), fp32 or bf16.
+ *
+ * It replaces, for this path only, what the reference does on the CPU in
+ *   nexar_video_aug.py:809-821  VideoTransform.forward        (driver, /255 rule)
+ *   nexar_video_aug.py:705-739  letterbox_resize               (+ tv F.resize antialias)
+ *   nexar_video_aug.py:746-755  horizontal_flip
+ *   nexar_video_aug.py:200-315  VideoAugmentation per-frame chain
+ *   nexar_video_aug.py:794-799  normalize_tensor
+ *   nexar_video_aug.py:407-424,464-482  resize_tensor / crop (dead-code variant)
+ *   nexar_videos.py:416-451     frame gather, THWC->CTHW permute, transform call
+ * The random decisions (nexar_video_aug.py:97-182, :748; nexar_videos.py:410)
+ * stay on the host, drawn from Python's `random` in the reference's order, and
+ * arrive here as one NexarClipParams per clip.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, no allocation inside
+ * nexar_clip_transform (the caller owns src, dst, params and workspace; only
+ * nexar_plan_create allocates, a few KB of device tables), asynchronous on the
+ * given CUDA stream.  Every function returns NEXAR_OK or a negative code;
+ * nexar_last_error() gives a thread-local message.
+ */
+#ifndef NEXAR_CLIP_TRANSFORM_H
+#define NEXAR_CLIP_TRANSFORM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEXAR_ABI_VERSION 1
+
+enum {
+  NEXAR_OK = 0,
+  NEXAR_ERR_INVALID = -1,     /* bad argument (the reference raises ValueError/TypeError) */
+  NEXAR_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  NEXAR_ERR_WORKSPACE = -3,   /* workspace too small / missing */
+  NEXAR_ERR_UNSUPPORTED = -4
+};
+
+enum { NEXAR_SRC_U8 = 0, NEXAR_SRC_F32 = 1 };              /* source frames: packed RGB, HWC */
+enum { NEXAR_DST_F32 = 0, NEXAR_DST_BF16 = 1 };
+
+/* NexarClipParams.flags */
+enum {
+  NEXAR_FLIP = 1u << 0,        /* nexar_video_aug.py:748 */
+  NEXAR_AUG = 1u << 1,         /* VideoAugmentation active and not skipped (:112) */
+  NEXAR_AFFINE = 1u << 2,      /* :130-136 */
+  NEXAR_GRAYSCALE = 1u << 3,   /* :139 */
+  NEXAR_NOISE = 1u << 4,       /* :140 */
+  NEXAR_BLUR = 1u << 5,        /* :141 */
+  NEXAR_POSTERIZE = 1u << 6,   /* :174 */
+  NEXAR_SOLARIZE = 1u << 7,    /* :173 */
+  NEXAR_INVERT = 1u << 8,      /* :172 */
+  NEXAR_CUTOUT = 1u << 9       /* :144 */
+};
+
+#define NEXAR_MAX_CUTOUT 8
+#define NEXAR_MAX_BLUR_TAPS 33
+
+/* Where the antialiased-resize output lands on the cs x cs canvas. */
+typedef struct NexarGeometry {
+  int32_t src_h, src_w;        /* decoded frame size */
+  int32_t canvas;              /* crop_size */
+  int32_t resize_h, resize_w;  /* size of the resize output (new_h, new_w) */
+  int32_t off_y, off_x;        /* canvas(y,x) = resized(y-off_y, x-off_x); letterbox: the pads; crop: -top,-left */
+} NexarGeometry;
+
+/* One per clip; every float already rounded the way torch rounds the Python
+ * double (float32 of the float64 value). */
+typedef struct NexarClipParams {
+  uint32_t flags;
+  int32_t crop_dy, crop_dx;    /* added to off_y/off_x: per-clip random crop (nexar_video_aug.py:472-473) */
+  float brightness;            /* ratio of tv _blend */
+  float contrast, contrast_q;  /* ratio and float32(1.0 - ratio) */
+  float saturation, saturation_q;
+  float hue;
+  float grid[6];               /* theta^T / [0.5w, 0.5h] of tv _gen_affine_grid: x' = gx(x,y) = x*grid[0]+y*grid[1]+grid[2]; y' likewise [3..5] */
+  float solarize_threshold;
+  int32_t posterize_bits;
+  float noise_level;
+  uint32_t noise_seed[2];
+  int32_t blur_ksize;          /* int(sigma*4)*2+1 */
+  float blur_taps[NEXAR_MAX_BLUR_TAPS]; /* tv _get_gaussian_kernel1d */
+  int32_t n_cutout;
+  int32_t cutout[NEXAR_MAX_CUTOUT][4]; /* top, left, height, width */
+} NexarClipParams;
+
+typedef struct NexarPlan NexarPlan;   /* geometry + device tap tables */
+
+typedef struct NexarTransformArgs {
+  uint32_t struct_size;         /* sizeof(NexarTransformArgs), for ABI checking */
+  int32_t n_clips, frames_per_clip;
+  const void* src;              /* device: base of the decoded frames */
+  const int64_t* frame_offsets; /* device [n_clips*frames_per_clip]: BYTE offset of each output frame's
+                                   source frame from src (temporal sampling = gather; repeats allowed) */
+  int64_t src_row_stride;       /* bytes between source rows */
+  const NexarClipParams* params;/* device [n_clips] */
+  uint32_t any_flags;           /* host hint: bitwise OR of params[i].flags; stages no clip needs are not launched */
+  void* dst;                    /* device */
+  int32_t dst_dtype;            /* NEXAR_DST_* */
+  int32_t normalize;            /* 0: leave values in [0,1] */
+  int64_t dst_stride[5];        /* ELEMENT strides for (clip, channel, frame, y, x) */
+  float mean[3], std[3];
+  void* workspace;              /* device, >= nexar_workspace_bytes(...) */
+  size_t workspace_bytes;
+  void* stream;                 /* cudaStream_t */
+} NexarTransformArgs;
+
+int nexar_abi_version(void);
+size_t nexar_sizeof_clip_params(void);     /* for binding checks */
+size_t nexar_sizeof_transform_args(void);
+const char* nexar_last_error(void);
+
+/* nexar_video_aug.py:713-719 (float64 truncation, floor-div pads) */
+int nexar_letterbox_geometry(int32_t src_h, int32_t src_w, int32_t crop_size, NexarGeometry* out);
+/* nexar_video_aug.py:411-415 then the centre crop of :468-469 */
+int nexar_resize_crop_geometry(int32_t src_h, int32_t src_w, int32_t size, int32_t crop_size, NexarGeometry* out);
+/* ATen _upsample_bilinear2d_aa tap table for one axis (host).  start/count: [out_size];
+ * weights: [out_size*kmax_capacity] row-major.  *kmax receives the table width used. */
+int nexar_aa_taps(int32_t in_size, int32_t out_size, int32_t* start, int32_t* count, float* weights,
+                  int32_t kmax_capacity, int32_t* kmax);
+
+int nexar_plan_create(const NexarGeometry* geom, int32_t src_dtype, NexarPlan** out);
+void nexar_plan_destroy(NexarPlan* plan);
+int nexar_plan_geometry(const NexarPlan* plan, NexarGeometry* out);
+
+/* Bytes of scratch nexar_clip_transform needs for this batch shape (covers the
+ * worst case: every clip augmented and blurred). */
+size_t nexar_workspace_bytes(const NexarPlan* plan, int32_t n_clips, int32_t frames_per_clip);
+
+/* The hot path.  Enqueues the kernels on args->stream and returns. */
+int nexar_clip_transform(const NexarPlan* plan, const NexarTransformArgs* args);
+
+/* Number of kernel launches the last nexar_clip_transform call on this thread enqueued. */
+int nexar_last_launch_count(void);
+
+/* Optional timing of the dominant (resize) kernel: after nexar_profile_begin(n) the next n calls record a
+ * CUDA event pair around that kernel on the call's stream; nexar_profile_end synchronises those events,
+ * writes up to `cap` per-call durations in ms and returns how many it wrote.  Used by bench.py. */
+int nexar_profile_begin(int32_t max_calls);
+int nexar_profile_end(float* ms_out, int32_t cap);
+
+/* Tuning knob for experiments: which resize kernel to use (0 = auto). */
+int nexar_set_resize_kernel(int32_t variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXAR_CLIP_TRANSFORM_H */

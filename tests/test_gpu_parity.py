@@ -1,0 +1,175 @@
+"""GPU parity: the CUDA path (through the C ABI) against the numpy oracle and the
+reference's frozen outputs.  Tolerances are north_star's: 1/255 max-abs before
+normalisation, 1e-3 after (asserted on the fp32 output); bf16 output is held to
+one bf16 ulp of the rounded oracle."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+from golden_util import case_names, load_case, special
+
+pytestmark = pytest.mark.gpu
+
+TOL_BEFORE = 1.0 / 255.0
+TOL_AFTER = 1e-3
+
+
+def _tf(kwargs, **extra):
+    from vision_collision_detection_b200 import create_video_transforms
+    return create_video_transforms(**kwargs, **extra)
+
+
+def _run(tf, clip_u8, params):
+    frames = torch.from_numpy(clip_u8).cuda().unsqueeze(0)
+    rec = dict(params)
+    rec.setdefault("crop", None)
+    out = tf.forward_batch(frames, params=[rec])
+    torch.cuda.synchronize()
+    return out[0].float().cpu().numpy()
+
+
+def _poster_ok(out, gold, tol, frac=5e-3):
+    return (np.abs(out - gold) > tol).mean() <= frac
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_matches_reference_golden(name):
+    c = load_case(name)
+    out = _run(_tf(c["kwargs"]), c["clip"], c["params"])
+    assert out.shape == c["out"].shape
+    tol = TOL_AFTER if c["cfg"].normalize else TOL_BEFORE
+    if name.startswith("poster"):
+        assert _poster_ok(out, c["out"], tol)
+    else:
+        assert np.abs(out - c["out"]).max() <= tol
+
+
+@pytest.mark.parametrize("name", ["val_small", "val_portrait", "val_upscale", "custom_small_s0", "ncwv_small_s2",
+                                  "allfx_small_s3", "allfx_small_s6"])
+def test_before_normalisation_within_one_255th(name):
+    c = load_case(name)
+    kw = dict(c["kwargs"], normalize=False)
+    out = _run(_tf(kw), c["clip"], c["params"])
+    want = O.apply_clip_transform(c["clip"].transpose(3, 0, 1, 2), c["cfg"], c["params"], stage="aug")
+    assert np.abs(out - want).max() <= TOL_BEFORE
+    assert np.abs(out - want).max() <= 1e-4          # in practice ~1e-6
+
+
+def test_reference_call_signature_and_rng_stream():
+    """transform(video[C,T,H,W] u8 view) -> [C,T,cs,cs] f32, drawing from ``random`` like the reference."""
+    c = load_case("custom_small_s1")
+    tf = _tf(c["kwargs"])
+    video = torch.from_numpy(c["clip"]).permute(3, 0, 1, 2)       # CPU, non-contiguous view
+    random.seed(c["random_seed"])
+    out = tf(video)
+    assert out.device.type == "cpu" and out.dtype == torch.float32 and tuple(out.shape) == c["out"].shape
+    assert np.abs(out.numpy() - c["out"]).max() <= TOL_AFTER
+    assert tf.last_params[0]["flip"] == c["params"]["flip"]
+    assert tf.last_params[0]["aug"] == c["params"]["aug"]          # bit-exact decisions
+    random.seed(c["random_seed"])
+    out_cuda = tf(video.cuda())
+    assert out_cuda.is_cuda and torch.equal(out_cuda.cpu(), out)
+
+
+def test_special_inputs_max_rule_and_float():
+    sp = special()
+    from vision_collision_detection_b200.synth import make_clip_np
+    tf = _tf(dict(mode="val", crop_size=56))
+    b01 = (make_clip_np(2, 96, 160, 50, "noise") & 1).astype(np.uint8)
+    out = tf(torch.from_numpy(b01).permute(3, 0, 1, 2)).numpy()
+    assert np.abs(out - sp["max1_u8"]).max() <= TOL_AFTER and out.max() > 1.0
+    z = torch.zeros(3, 2, 96, 160, dtype=torch.uint8)
+    assert np.abs(tf(z).numpy() - sp["zeros_u8"]).max() <= TOL_AFTER
+    f01 = torch.from_numpy(make_clip_np(2, 96, 160, 51, "dashcam").astype(np.float32) / 255.0).permute(3, 0, 1, 2)
+    assert np.abs(tf(f01).numpy() - sp["float01"]).max() <= TOL_AFTER
+    f255 = torch.from_numpy(make_clip_np(2, 96, 160, 52, "dashcam").astype(np.float32)).permute(3, 0, 1, 2)
+    assert np.abs(tf(f255).numpy() - sp["float255"]).max() <= TOL_AFTER
+
+
+def test_mixed_batch_max_rule_is_per_clip():
+    """One all-{0,1} clip inside a normal batch: only that clip skips the /255."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    a = make_clip_np(2, 96, 160, 60, "dashcam")
+    b = (make_clip_np(2, 96, 160, 61, "noise") & 1).astype(np.uint8)
+    tf = _tf(dict(mode="val", crop_size=56))
+    out = tf.forward_batch(torch.from_numpy(np.stack([a, b, a])).cuda()).cpu().numpy()
+    cfg = O.TransformConfig(mode="val", crop_size=56)
+    nop = {"flip": False, "aug": None}
+    for i, clip in enumerate([a, b, a]):
+        want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, nop)
+        assert np.abs(out[i] - want).max() <= TOL_AFTER
+
+
+def test_resize_crop_variant():
+    """R11: short side -> size, centre / random crop (bit-exact offsets from the same seed)."""
+    from vision_collision_detection_b200 import create_video_transform
+    from vision_collision_detection_b200.synth import make_clip_np
+    from golden_util import META
+    sp = special()
+    clip = make_clip_np(2, 96, 160, 53, "dashcam")
+    video = torch.from_numpy(clip).permute(3, 0, 1, 2)
+    tfc = create_video_transform(mode="val", min_size=56, crop_size=56, normalize=False, use_letterbox=False)
+    assert np.abs(tfc(video).numpy() - sp["r11_center"]).max() <= TOL_BEFORE
+    tfr = create_video_transform(mode="train", min_size=56, max_size=None, crop_size=56, normalize=False,
+                                 use_letterbox=False, horizontal_flip_prob=0.0)
+    random.seed(11)
+    out = tfr(video).numpy()
+    assert tfr.last_params[0]["crop_top_left"] == (0, META["r11_random_left"])
+    assert np.abs(out - sp["r11_random"]).max() <= TOL_BEFORE
+
+
+def test_bf16_output_and_layouts():
+    c = load_case("custom_small_s2")
+    want = torch.from_numpy(c["out"])
+    tf = _tf(c["kwargs"])
+    frames = torch.from_numpy(c["clip"]).cuda().unsqueeze(0)
+    rec = dict(c["params"], crop=None)
+    ref32 = tf.forward_batch(frames, params=[rec])[0]
+    o16 = tf.forward_batch(frames, params=[rec], out_dtype=torch.bfloat16)[0]
+    assert o16.dtype == torch.bfloat16
+    assert torch.equal(o16, ref32.to(torch.bfloat16))             # same fp32 value, RNE
+    # within one bf16 ulp of the rounded oracle
+    w16 = want.to(torch.bfloat16).float()
+    ulp = torch.maximum(w16.abs(), torch.tensor(2.0 ** -6)) * 2.0 ** -7
+    assert ((o16.float().cpu() - w16).abs() <= ulp + 1e-3).all()
+    bt = tf.forward_batch(frames, params=[rec], layout="BTCHW")[0]        # [T,C,H,W]
+    assert torch.equal(bt.permute(1, 0, 2, 3), ref32)
+    bl = tf.forward_batch(frames, params=[rec], layout="BTHWC")[0]        # [T,H,W,C] (Dataset layout)
+    assert torch.equal(bl.permute(3, 0, 1, 2), ref32)
+
+
+def test_frame_gather_equals_copy():
+    """Temporal sampling by index gather (repeat-last-frame padding included) == materialised clip."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    pool = make_clip_np(7, 96, 160, 70, "dashcam")
+    idx = [2, 3, 4, 5, 6, 6, 6, 6]
+    tf = _tf(dict(mode="val", crop_size=56))
+    a = tf.forward_batch(torch.from_numpy(pool[idx]).cuda().unsqueeze(0))
+    b = tf.forward_batch(torch.from_numpy(pool).cuda().unsqueeze(0), frame_index=torch.tensor([idx]))
+    assert torch.equal(a, b)
+
+
+def test_full_size_properties():
+    """BASELINE cfg2 frame size (720p -> 224): size-independent properties on the device."""
+    from vision_collision_detection_b200.synth import make_clip_torch
+    clips = torch.stack([make_clip_torch(4, 720, 1280, s, "dashcam") for s in range(3)])
+    tf = _tf(dict(mode="train"))
+    recs = [{"flip": f, "aug": None, "crop": None} for f in (False, True, False)]
+    out = tf.forward_batch(clips, params=recs)
+    assert tuple(out.shape) == (3, 3, 4, 224, 224)
+    assert torch.all(out[:, :, :, :49] == -2.0) and torch.all(out[:, :, :, 174:] == -2.0)   # 49 / 50 pad rows
+    assert out[:, :, :, 49:174].min() > -2.0
+    # flip is an exact mirror of the un-flipped result
+    noflip = tf.forward_batch(clips[1:2], params=[{"flip": False, "aug": None, "crop": None}])
+    assert torch.equal(out[1:2], noflip.flip(-1))
+    # constant frames stay constant through the antialiased resize (weights sum to one)
+    const = torch.full((1, 2, 720, 1280, 3), 200, dtype=torch.uint8, device="cuda")
+    oc = tf.forward_batch(const, params=[{"flip": False, "aug": None, "crop": None}])
+    want = (200.0 / 255.0 - 0.45) / 0.225
+    assert (oc[:, :, :, 49:174] - want).abs().max() <= 1e-5
+    # idempotence / determinism
+    assert torch.equal(out, tf.forward_batch(clips, params=recs))

@@ -1,0 +1,873 @@
+// clip_transform.cu — sm_100a kernels + C ABI of libnexar_clip_b200.so.
+//
+// Path (reference file:line in include/nexar_clip_transform.h):
+//   K1 resize   : uint8 THWC frames -> antialiased separable resample -> either the
+//                 final normalised tensor (no augmentation) or a brightness-adjusted
+//                 fp32 RGBX intermediate + per-band gray sums (augmentation).
+//   K2 colour   : contrast (needs the frame's gray mean) -> saturation -> hue, in place.
+//   K3 geometry : affine gather with the fill=0 mask quirk, effects, normalise, store.
+//   K4 blur     : only when blur_sigma > 0 (reflect-padded gaussian, then the rest of the chain).
+// The /255 decision of VideoTransform.forward is clip-global and data dependent
+// (nexar_video_aug.py:814): K1 runs assuming "max > 1", records the clip maximum, and
+// a second, normally empty, launch redoes the clips whose maximum was <= 1.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nexar_clip_transform.h"
+
+// ---------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local int g_launches = 0;
+static int g_resize_variant = 0;
+
+static std::vector<cudaEvent_t> g_prof_ev;
+static int g_prof_n = 0;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(NEXAR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------
+struct DevPlan {
+  int src_h, src_w, cs, rh, rw, off_y, off_x, ky, kx;
+  const int* ystart;
+  const int* ycount;
+  const float* ywt;
+  const int* xstart;
+  const int* xcount;
+  const float* xwt;
+};
+
+struct NexarPlan {
+  NexarGeometry g;
+  int src_dtype;
+  DevPlan d;
+  void* dev_tables;
+  std::vector<int> ystart, ycount, xstart, xcount;
+  std::vector<float> ywt, xwt;
+};
+
+// ATen UpSampleKernel.cpp _compute_indices_min_size_weights_aa, float opmath.
+static void aa_taps_host(int in_size, int out_size, std::vector<int>& start, std::vector<int>& count,
+                         std::vector<float>& wts, int& kmax) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  kmax = (int)std::ceil(support) * 2 + 1;
+  start.assign(out_size, 0);
+  count.assign(out_size, 0);
+  wts.assign((size_t)out_size * kmax, 0.0f);
+  for (int i = 0; i < out_size; ++i) {
+    const float center = scale * ((float)i + 0.5f);
+    int lo = (int)(center - support + 0.5f);
+    if (lo < 0) lo = 0;
+    int hi = (int)(center + support + 0.5f);
+    if (hi > in_size) hi = in_size;
+    int n = hi - lo;
+    if (n < 0) n = 0;
+    if (n > kmax) n = kmax;
+    float total = 0.0f;
+    float* w = &wts[(size_t)i * kmax];
+    for (int j = 0; j < n; ++j) {
+      float x = ((float)(j + lo) - center + 0.5f) * invscale;
+      x = std::fabs(x);
+      w[j] = x < 1.0f ? 1.0f - x : 0.0f;
+      total += w[j];
+    }
+    if (total != 0.0f)
+      for (int j = 0; j < n; ++j) w[j] /= total;
+    start[i] = lo;
+    count[i] = n;
+  }
+}
+
+extern "C" int nexar_abi_version(void) { return NEXAR_ABI_VERSION; }
+extern "C" size_t nexar_sizeof_clip_params(void) { return sizeof(NexarClipParams); }
+extern "C" size_t nexar_sizeof_transform_args(void) { return sizeof(NexarTransformArgs); }
+extern "C" const char* nexar_last_error(void) { return g_err.c_str(); }
+extern "C" int nexar_last_launch_count(void) { return g_launches; }
+extern "C" int nexar_set_resize_kernel(int32_t v) {
+  g_resize_variant = v;
+  return NEXAR_OK;
+}
+
+extern "C" int nexar_profile_begin(int32_t max_calls) {
+  for (cudaEvent_t e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  g_prof_n = 0;
+  for (int i = 0; i < 2 * max_calls; ++i) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    g_prof_ev.push_back(e);
+  }
+  return NEXAR_OK;
+}
+extern "C" int nexar_profile_end(float* ms_out, int32_t cap) {
+  int n = 0;
+  for (int i = 0; i < g_prof_n && n < cap; ++i) {
+    if (cudaEventSynchronize(g_prof_ev[2 * i + 1]) != cudaSuccess) break;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) != cudaSuccess) break;
+    ms_out[n++] = ms;
+  }
+  for (cudaEvent_t e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  g_prof_n = 0;
+  return n;
+}
+
+extern "C" int nexar_letterbox_geometry(int32_t h, int32_t w, int32_t cs, NexarGeometry* out) {
+  if (!out || h <= 0 || w <= 0 || cs <= 0) return fail(NEXAR_ERR_INVALID, "letterbox_geometry: bad size");
+  const double sh = (double)cs / (double)h, sw = (double)cs / (double)w;
+  const double scale = sh < sw ? sh : sw;
+  out->src_h = h;
+  out->src_w = w;
+  out->canvas = cs;
+  out->resize_h = (int32_t)((double)h * scale);  // python int(): truncation of the float64 product
+  out->resize_w = (int32_t)((double)w * scale);
+  out->off_y = (cs - out->resize_h) / 2;         // both non-negative here, so / == python //
+  out->off_x = (cs - out->resize_w) / 2;
+  if (out->resize_h <= 0 || out->resize_w <= 0)
+    return fail(NEXAR_ERR_INVALID, "letterbox_geometry: resized size is zero (torch would raise)");
+  return NEXAR_OK;
+}
+
+static int floordiv(int a, int b) {  // python // for b > 0
+  int q = a / b;
+  if ((a % b != 0) && (a < 0)) --q;
+  return q;
+}
+
+extern "C" int nexar_resize_crop_geometry(int32_t h, int32_t w, int32_t size, int32_t cs, NexarGeometry* out) {
+  if (!out || h <= 0 || w <= 0 || cs <= 0 || size <= 0) return fail(NEXAR_ERR_INVALID, "resize_crop_geometry: bad size");
+  out->src_h = h;
+  out->src_w = w;
+  out->canvas = cs;
+  if (h > w) {
+    out->resize_h = (int32_t)((int64_t)size * h / w);
+    out->resize_w = size;
+  } else {
+    out->resize_h = size;
+    out->resize_w = (int32_t)((int64_t)size * w / h);
+  }
+  if (out->resize_h < cs || out->resize_w < cs)
+    return fail(NEXAR_ERR_INVALID, "resize_crop_geometry: resized frame smaller than crop_size");
+  out->off_y = -floordiv(out->resize_h - cs, 2);
+  out->off_x = -floordiv(out->resize_w - cs, 2);
+  return NEXAR_OK;
+}
+
+extern "C" int nexar_aa_taps(int32_t in_size, int32_t out_size, int32_t* start, int32_t* count, float* weights,
+                             int32_t cap, int32_t* kmax) {
+  if (in_size <= 0 || out_size <= 0 || !start || !count || !weights || !kmax)
+    return fail(NEXAR_ERR_INVALID, "aa_taps: bad argument");
+  std::vector<int> s, c;
+  std::vector<float> w;
+  int k = 0;
+  aa_taps_host(in_size, out_size, s, c, w, k);
+  if (k > cap) return fail(NEXAR_ERR_INVALID, "aa_taps: kmax_capacity too small");
+  *kmax = k;
+  for (int i = 0; i < out_size; ++i) {
+    start[i] = s[i];
+    count[i] = c[i];
+    for (int j = 0; j < cap; ++j) weights[(size_t)i * cap + j] = j < k ? w[(size_t)i * k + j] : 0.0f;
+  }
+  return NEXAR_OK;
+}
+
+extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, NexarPlan** out) {
+  if (!g || !out) return fail(NEXAR_ERR_INVALID, "plan_create: null argument");
+  if (src_dtype != NEXAR_SRC_U8 && src_dtype != NEXAR_SRC_F32) return fail(NEXAR_ERR_INVALID, "plan_create: bad src_dtype");
+  if (g->src_h <= 0 || g->src_w <= 0 || g->canvas <= 0 || g->resize_h <= 0 || g->resize_w <= 0)
+    return fail(NEXAR_ERR_INVALID, "plan_create: bad geometry");
+  NexarPlan* p = new NexarPlan();
+  p->g = *g;
+  p->src_dtype = src_dtype;
+  int ky = 0, kx = 0;
+  aa_taps_host(g->src_h, g->resize_h, p->ystart, p->ycount, p->ywt, ky);
+  aa_taps_host(g->src_w, g->resize_w, p->xstart, p->xcount, p->xwt, kx);
+  const size_t ni = (size_t)(g->resize_h + g->resize_w) * 2 * sizeof(int);
+  const size_t nf = ((size_t)g->resize_h * ky + (size_t)g->resize_w * kx) * sizeof(float);
+  p->dev_tables = nullptr;
+  cudaError_t e = cudaMalloc(&p->dev_tables, ni + nf);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(NEXAR_ERR_CUDA, std::string("plan_create: cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  std::vector<char> host(ni + nf);
+  int* hi = (int*)host.data();
+  memcpy(hi, p->ystart.data(), g->resize_h * sizeof(int));
+  memcpy(hi + g->resize_h, p->ycount.data(), g->resize_h * sizeof(int));
+  memcpy(hi + 2 * g->resize_h, p->xstart.data(), g->resize_w * sizeof(int));
+  memcpy(hi + 2 * g->resize_h + g->resize_w, p->xcount.data(), g->resize_w * sizeof(int));
+  float* hf = (float*)(host.data() + ni);
+  memcpy(hf, p->ywt.data(), p->ywt.size() * sizeof(float));
+  memcpy(hf + p->ywt.size(), p->xwt.data(), p->xwt.size() * sizeof(float));
+  e = cudaMemcpy(p->dev_tables, host.data(), ni + nf, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(p->dev_tables);
+    delete p;
+    return fail(NEXAR_ERR_CUDA, std::string("plan_create: cudaMemcpy: ") + cudaGetErrorString(e));
+  }
+  int* di = (int*)p->dev_tables;
+  float* df = (float*)((char*)p->dev_tables + ni);
+  DevPlan& d = p->d;
+  d.src_h = g->src_h;
+  d.src_w = g->src_w;
+  d.cs = g->canvas;
+  d.rh = g->resize_h;
+  d.rw = g->resize_w;
+  d.off_y = g->off_y;
+  d.off_x = g->off_x;
+  d.ky = ky;
+  d.kx = kx;
+  d.ystart = di;
+  d.ycount = di + g->resize_h;
+  d.xstart = di + 2 * g->resize_h;
+  d.xcount = di + 2 * g->resize_h + g->resize_w;
+  d.ywt = df;
+  d.xwt = df + p->ywt.size();
+  *out = p;
+  return NEXAR_OK;
+}
+
+extern "C" void nexar_plan_destroy(NexarPlan* p) {
+  if (!p) return;
+  if (p->dev_tables) cudaFree(p->dev_tables);
+  delete p;
+}
+
+extern "C" int nexar_plan_geometry(const NexarPlan* p, NexarGeometry* out) {
+  if (!p || !out) return fail(NEXAR_ERR_INVALID, "plan_geometry: null argument");
+  *out = p->g;
+  return NEXAR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+static const int kMaxBands = 16;
+
+struct Workspace {
+  unsigned* clip_max;   // [n_clips] order-preserving uint image of the float maximum
+  float* gray_partial;  // [2][n_frames][kMaxBands]
+  float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
+  float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
+  size_t total;
+};
+
+static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base) {
+  Workspace w;
+  const size_t nf = (size_t)n_clips * T;
+  const int bh = imin(p->g.resize_h, p->g.canvas), bw = imin(p->g.resize_w, p->g.canvas);
+  size_t off = 0;
+  char* b = (char*)base;
+  w.clip_max = (unsigned*)(b + off);
+  off = align_up(off + (size_t)n_clips * sizeof(unsigned), 256);
+  w.gray_partial = (float*)(b + off);
+  off = align_up(off + 2 * nf * kMaxBands * sizeof(float), 256);
+  w.inter = (float4*)(b + off);
+  off = align_up(off + nf * bh * bw * sizeof(float4), 256);
+  w.canvas = (float*)(b + off);
+  off = align_up(off + nf * 3 * (size_t)p->g.canvas * p->g.canvas * sizeof(float), 256);
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t nexar_workspace_bytes(const NexarPlan* p, int32_t n_clips, int32_t T) {
+  if (!p || n_clips <= 0 || T <= 0) return 0;
+  return carve(p, n_clips, T, nullptr).total;
+}
+
+// ---------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------
+struct KArgs {
+  const void* src;
+  const int64_t* frame_offsets;
+  int64_t src_row_stride;
+  const NexarClipParams* params;
+  void* dst;
+  int64_t sb, sc, st, sy, sx;
+  int T;
+  int normalize;
+  float nscale[3], nbias[3];  // out = v * nscale + nbias  ((v - mean) / std)
+  unsigned* clip_max;
+  float* gray_partial;
+  float4* inter;
+  float* canvas;
+  int n_frames;
+  int bh, bw;  // allocation dims of one intermediate frame
+  int pass;    // 0: assume /255 and record max; 1: redo clips whose max <= 1 without scaling; 2: max already known
+};
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+// tv rgb_to_grayscale: (0.2989 r + 0.587 g) + 0.114 b, every product rounded (no fma contraction)
+__device__ __forceinline__ float gray_of(float r, float g, float b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+// tv _blend: (ratio*a + q*b).clamp(0,1)
+__device__ __forceinline__ float blend(float a, float b, float r, float q) {
+  return clamp01(__fadd_rn(__fmul_rn(r, a), __fmul_rn(q, b)));
+}
+
+template <typename T>
+__device__ __forceinline__ void store_out(void* dst, int64_t idx, float v);
+template <>
+__device__ __forceinline__ void store_out<float>(void* dst, int64_t idx, float v) {
+  ((float*)dst)[idx] = v;
+}
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(void* dst, int64_t idx, float v) {
+  ((__nv_bfloat16*)dst)[idx] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = 0.0f;
+  if (wid == 0) {
+    t = lane < nw ? red[lane] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in warp 0
+}
+
+// Visible box of one clip: canvas rows [by0,by1) x cols [bx0,bx1) hold resized rows
+// [i_lo,i_hi) x cols [j_lo,j_hi) (mirrored in x when the clip is flipped).
+struct Box {
+  int oy, ox, i_lo, i_hi, j_lo, j_hi, by0, by1, bx0, bx1;
+};
+__device__ __forceinline__ Box clip_box(const DevPlan& P, int crop_dy, int crop_dx, bool flip) {
+  Box b;
+  b.oy = P.off_y + crop_dy;
+  b.ox = P.off_x + crop_dx;
+  b.i_lo = max(0, -b.oy);
+  b.i_hi = max(b.i_lo, min(P.rh, P.cs - b.oy));
+  b.j_lo = max(0, -b.ox);
+  b.j_hi = max(b.j_lo, min(P.rw, P.cs - b.ox));
+  b.by0 = b.i_lo + b.oy;
+  b.by1 = b.i_hi + b.oy;
+  if (!flip) {
+    b.bx0 = b.j_lo + b.ox;
+    b.bx1 = b.j_hi + b.ox;
+  } else {
+    b.bx0 = P.cs - (b.j_hi + b.ox);
+    b.bx1 = P.cs - (b.j_lo + b.ox);
+  }
+  return b;
+}
+
+// ---------------------------------------------------------------------------------
+// K0: clip maximum (only for crop geometries, where K1 does not read every source pixel)
+// ---------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void clip_max_kernel(DevPlan P, KArgs A) {
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const char* base = (const char*)A.src + A.frame_offsets[frame];
+  const int n = P.src_w * 3;
+  float m = -INFINITY;
+  for (int y = blockIdx.x; y < P.src_h; y += gridDim.x) {
+    const SrcT* row = (const SrcT*)(base + (int64_t)y * A.src_row_stride);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) m = fmaxf(m, (float)row[e]);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&A.clip_max[clip], ordered_bits(m));
+}
+
+// ---------------------------------------------------------------------------------
+// K1 (general variant): output-stationary separable resample.  Any geometry
+// (down- or up-scale, any width), uint8 or float32 source.
+// ---------------------------------------------------------------------------------
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A) {
+  extern __shared__ float vbuf[];  // [src_w*3] vertical-pass result of the current resized row
+  __shared__ float red[32];
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const int t = frame - clip * A.T;
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  float scale;
+  if (A.pass == 0) {
+    scale = 1.0f / 255.0f;
+  } else {
+    const bool big = ordered_to_float(A.clip_max[clip]) > 1.0f;
+    if (A.pass == 1 && big) return;
+    scale = big ? 1.0f / 255.0f : 1.0f;
+  }
+  const bool flip = flags & NEXAR_FLIP, aug = flags & NEXAR_AUG;
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flip);
+  const int nb = gridDim.x, band = blockIdx.x;
+  const int per = (B.i_hi - B.i_lo + nb - 1) / nb;
+  const int i0 = min(B.i_hi, B.i_lo + band * per), i1 = min(B.i_hi, i0 + per);
+  const char* fbase = (const char*)A.src + A.frame_offsets[frame];
+  const int W3 = P.src_w * 3;
+  const float bright = cp->brightness;
+  float nsc[3], nbi[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    nsc[c] = A.normalize ? A.nscale[c] : 1.0f;
+    nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
+  }
+  const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
+  float vmax = -INFINITY, gsum = 0.0f;
+
+  for (int i = i0; i < i1; ++i) {
+    const int ys = P.ystart[i], yc = P.ycount[i];
+    const float* wy = P.ywt + (size_t)i * P.ky;
+    for (int e = threadIdx.x; e < W3; e += blockDim.x) {
+      float acc = 0.0f;
+      for (int k = 0; k < yc; ++k) {
+        const float v = (float)((const SrcT*)(fbase + (int64_t)(ys + k) * A.src_row_stride))[e];
+        vmax = fmaxf(vmax, v);
+        acc = fmaf(wy[k], v, acc);
+      }
+      vbuf[e] = acc;
+    }
+    __syncthreads();
+    const int y = i + B.oy;
+    for (int j = B.j_lo + threadIdx.x; j < B.j_hi; j += blockDim.x) {
+      const int xs = P.xstart[j], xc = P.xcount[j];
+      const float* wx = P.xwt + (size_t)j * P.kx;
+      float r = 0.0f, g = 0.0f, b = 0.0f;
+      for (int k = 0; k < xc; ++k) {
+        const float w = wx[k];
+        const float* p = vbuf + (xs + k) * 3;
+        r = fmaf(w, p[0], r);
+        g = fmaf(w, p[1], g);
+        b = fmaf(w, p[2], b);
+      }
+      r *= scale;
+      g *= scale;
+      b *= scale;
+      int x = j + B.ox;
+      if (flip) x = P.cs - 1 - x;
+      if (aug) {
+        r = clamp01(__fmul_rn(bright, r));
+        g = clamp01(__fmul_rn(bright, g));
+        b = clamp01(__fmul_rn(bright, b));
+        gsum += gray_of(r, g, b);
+        A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (x - B.bx0)] = make_float4(r, g, b, 0.0f);
+      } else {
+        const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+        store_out<DstT>(A.dst, o, fmaf(r, nsc[0], nbi[0]));
+        store_out<DstT>(A.dst, o + A.sc, fmaf(g, nsc[1], nbi[1]));
+        store_out<DstT>(A.dst, o + 2 * A.sc, fmaf(b, nsc[2], nbi[2]));
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!aug) {
+    // zero-padded canvas outside the box -> normalised pad value
+    const int Y0 = band == 0 ? 0 : i0 + B.oy;
+    const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
+    const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;  // content rows of this band
+    for (int y = Y0; y < Y1; ++y) {
+      const bool content_row = (y >= cy0 && y < cy1);
+      for (int x = threadIdx.x; x < P.cs; x += blockDim.x) {
+        if (content_row && x >= B.bx0 && x < B.bx1) continue;
+        const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+      }
+    }
+  }
+
+  if (A.pass == 0) {
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&A.clip_max[clip], ordered_bits(vmax));
+  }
+  if (aug) {
+    const float s = block_sum(gsum, red);
+    if (threadIdx.x == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// colour chain on one pixel: contrast -> saturation -> hue  (tv:_functional_tensor.py:181-321)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void hue_shift(float& r, float& g, float& b, float hue) {
+  const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+  const bool eqc = maxc == minc;
+  const float cr = __fsub_rn(maxc, minc);
+  const float s = __fdiv_rn(cr, eqc ? 1.0f : maxc);
+  const float div = eqc ? 1.0f : cr;
+  const float rc = __fdiv_rn(__fsub_rn(maxc, r), div);
+  const float gc = __fdiv_rn(__fsub_rn(maxc, g), div);
+  const float bc = __fdiv_rn(__fsub_rn(maxc, b), div);
+  float h;
+  if (maxc == r)
+    h = __fsub_rn(bc, gc);
+  else if (maxc == g)
+    h = __fsub_rn(__fadd_rn(2.0f, rc), bc);
+  else
+    h = __fsub_rn(__fadd_rn(4.0f, gc), rc);
+  h = fmodf(__fadd_rn(__fdiv_rn(h, 6.0f), 1.0f), 1.0f);
+  // (h + hue) % 1.0 — python-style remainder (ATen remainder: fmod, then fix the sign)
+  float hh = fmodf(__fadd_rn(h, hue), 1.0f);
+  if (hh != 0.0f && hh < 0.0f) hh = __fadd_rn(hh, 1.0f);
+  const float v = maxc;
+  const float h6 = __fmul_rn(hh, 6.0f);
+  const float fi = floorf(h6);
+  const float f = __fsub_rn(h6, fi);
+  int i = (int)fi % 6;
+  if (i < 0) i += 6;
+  const float p = clamp01(__fmul_rn(v, __fsub_rn(1.0f, s)));
+  const float q = clamp01(__fmul_rn(v, __fsub_rn(1.0f, __fmul_rn(s, f))));
+  const float tt = clamp01(__fmul_rn(v, __fsub_rn(1.0f, __fmul_rn(s, __fsub_rn(1.0f, f)))));
+  switch (i) {
+    case 0: r = v; g = tt; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = tt; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = tt; g = p; b = v; break;
+    default: r = v; g = p; b = q; break;
+  }
+}
+
+__device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const NexarClipParams* cp, float mean) {
+  r = blend(r, mean, cp->contrast, cp->contrast_q);
+  g = blend(g, mean, cp->contrast, cp->contrast_q);
+  b = blend(b, mean, cp->contrast, cp->contrast_q);
+  const float gy = gray_of(r, g, b);
+  r = blend(r, gy, cp->saturation, cp->saturation_q);
+  g = blend(g, gy, cp->saturation, cp->saturation_q);
+  b = blend(b, gy, cp->saturation, cp->saturation_q);
+  hue_shift(r, g, b, cp->hue);
+}
+
+__device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, int frame, int slot, int nbands) {
+  const float* gp = A.gray_partial + ((size_t)slot * A.n_frames + frame) * kMaxBands;
+  float s = 0.0f;
+  for (int b = 0; b < nbands; ++b) s += gp[b];
+  return s / (float)(P.cs * P.cs);
+}
+
+// K2: contrast/saturation/hue in place on the content box.
+__global__ void __launch_bounds__(256) colour_kernel(DevPlan P, KArgs A, int nbands) {
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const NexarClipParams* cp = A.params + clip;
+  if (!(cp->flags & NEXAR_AUG)) return;
+  const int slot = ordered_to_float(A.clip_max[clip]) > 1.0f ? 0 : 1;
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, cp->flags & NEXAR_FLIP);
+  const int h = B.by1 - B.by0, w = B.bx1 - B.bx0;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * w) return;
+  const float mean = frame_mean(A, P, frame, slot, nbands);
+  const int y = idx / w, x = idx - y * w;
+  float4* p = A.inter + ((size_t)frame * A.bh + y) * A.bw + x;
+  float4 v = *p;
+  colour_chain(v.x, v.y, v.z, cp, mean);
+  *p = v;
+}
+
+// ---------------------------------------------------------------------------------
+// K3: affine gather + effects + normalise + store
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash_u32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// counter-based standard normal (statistical stand-in for torch.randn_like, nexar_video_aug.py:245)
+__device__ __forceinline__ float gauss_noise(unsigned s0, unsigned s1, unsigned idx) {
+  const unsigned a = hash_u32(idx * 2u + s0), b = hash_u32((idx * 2u + 1u) ^ s1);
+  const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__device__ __forceinline__ void point_effects(float& r, float& g, float& b, const NexarClipParams* cp, unsigned flags,
+                                              int y, int x) {
+  if (flags & NEXAR_POSTERIZE) {
+    const unsigned mask = (0xFFu << (8 - cp->posterize_bits)) & 0xFFu;
+    r = __fdiv_rn((float)((unsigned)__fmul_rn(r, 255.0f) & mask), 255.0f);
+    g = __fdiv_rn((float)((unsigned)__fmul_rn(g, 255.0f) & mask), 255.0f);
+    b = __fdiv_rn((float)((unsigned)__fmul_rn(b, 255.0f) & mask), 255.0f);
+  }
+  if (flags & NEXAR_SOLARIZE) {
+    const float th = cp->solarize_threshold;
+    r = r >= th ? __fsub_rn(1.0f, r) : r;
+    g = g >= th ? __fsub_rn(1.0f, g) : g;
+    b = b >= th ? __fsub_rn(1.0f, b) : b;
+  }
+  if (flags & NEXAR_INVERT) {
+    r = __fsub_rn(1.0f, r);
+    g = __fsub_rn(1.0f, g);
+    b = __fsub_rn(1.0f, b);
+  }
+  if (flags & NEXAR_CUTOUT) {
+    for (int k = 0; k < cp->n_cutout; ++k) {
+      const int top = cp->cutout[k][0], left = cp->cutout[k][1];
+      if (y >= top && y < top + cp->cutout[k][2] && x >= left && x < left + cp->cutout[k][3]) r = g = b = 0.0f;
+    }
+  }
+}
+
+template <typename DstT>
+__global__ void __launch_bounds__(256) geometry_kernel(DevPlan P, KArgs A, int nbands) {
+  __shared__ float padc[3];
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const int t = frame - clip * A.T;
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  if (!(flags & NEXAR_AUG)) return;
+  const int slot = ordered_to_float(A.clip_max[clip]) > 1.0f ? 0 : 1;
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flags & NEXAR_FLIP);
+  const int cs = P.cs;
+  if (threadIdx.x == 0) {
+    // colour of a zero (pad) pixel after brightness/contrast/saturation/hue
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    colour_chain(r, g, b, cp, frame_mean(A, P, frame, slot, nbands));
+    padc[0] = r; padc[1] = g; padc[2] = b;
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cs * cs) return;
+  const int y = idx / cs, x = idx - y * cs;
+  const float4* fr = A.inter + (size_t)frame * A.bh * A.bw;
+  auto fetch = [&](int yy, int xx, float& r, float& g, float& b) {
+    if (yy >= B.by0 && yy < B.by1 && xx >= B.bx0 && xx < B.bx1) {
+      const float4 v = fr[(size_t)(yy - B.by0) * A.bw + (xx - B.bx0)];
+      r = v.x; g = v.y; b = v.z;
+    } else {
+      r = padc[0]; g = padc[1]; b = padc[2];
+    }
+  };
+  float r, g, b;
+  if (flags & NEXAR_AFFINE) {
+    const float xb = (float)x - (float)cs * 0.5f + 0.5f, yb = (float)y - (float)cs * 0.5f + 0.5f;
+    const float gx = __fadd_rn(__fadd_rn(__fmul_rn(xb, cp->grid[0]), __fmul_rn(yb, cp->grid[1])), cp->grid[2]);
+    const float gy = __fadd_rn(__fadd_rn(__fmul_rn(xb, cp->grid[3]), __fmul_rn(yb, cp->grid[4])), cp->grid[5]);
+    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)cs), 1.0f), 2.0f);
+    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)cs), 1.0f), 2.0f);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = __fsub_rn(ix, x0f), wy1 = __fsub_rn(iy, y0f);
+    const float wx0 = __fsub_rn(1.0f, wx1), wy0 = __fsub_rn(1.0f, wy1);
+    // clamp before the int cast so wild matrices cannot overflow
+    const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)cs + 1.0f);
+    const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)cs + 1.0f);
+    r = g = b = 0.0f;
+    float m = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = x0 + dx, yy = y0 + dy;
+        if (xx >= 0 && xx < cs && yy >= 0 && yy < cs) {
+          const float w = __fmul_rn(dx ? wx1 : wx0, dy ? wy1 : wy0);
+          float pr, pg, pb;
+          fetch(yy, xx, pr, pg, pb);
+          r = fmaf(pr, w, r);
+          g = fmaf(pg, w, g);
+          b = fmaf(pb, w, b);
+          m += w;
+        }
+      }
+    r = __fmul_rn(r, m);  // img * mask + (1 - mask) * 0
+    g = __fmul_rn(g, m);
+    b = __fmul_rn(b, m);
+  } else {
+    fetch(y, x, r, g, b);
+  }
+  if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+  if (flags & NEXAR_NOISE) {
+    const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
+    r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+    g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
+    b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+  }
+  if (flags & NEXAR_BLUR) {
+    float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+    cv[idx] = r;
+    cv[cs * cs + idx] = g;
+    cv[2 * cs * cs + idx] = b;
+    return;
+  }
+  point_effects(r, g, b, cp, flags, y, x);
+  const int64_t o = (int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)y * A.sy + (int64_t)x * A.sx;
+  if (A.normalize) {
+    r = fmaf(r, A.nscale[0], A.nbias[0]);
+    g = fmaf(g, A.nscale[1], A.nbias[1]);
+    b = fmaf(b, A.nscale[2], A.nbias[2]);
+  }
+  store_out<DstT>(A.dst, o, r);
+  store_out<DstT>(A.dst, o + A.sc, g);
+  store_out<DstT>(A.dst, o + 2 * A.sc, b);
+}
+
+// K4: gaussian blur (tv gaussian_blur: reflect pad, outer-product kernel) + rest of the chain.
+template <typename DstT>
+__global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const int t = frame - clip * A.T;
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  if (!(flags & NEXAR_AUG) || !(flags & NEXAR_BLUR)) return;
+  const int cs = P.cs;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cs * cs) return;
+  const int y = idx / cs, x = idx - y * cs;
+  const int k = cp->blur_ksize, h = k / 2;
+  const float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  for (int dy = 0; dy < k; ++dy) {
+    int yy = y + dy - h;
+    yy = yy < 0 ? -yy : (yy >= cs ? 2 * cs - 2 - yy : yy);
+    const float wyv = cp->blur_taps[dy];
+    for (int dx = 0; dx < k; ++dx) {
+      int xx = x + dx - h;
+      xx = xx < 0 ? -xx : (xx >= cs ? 2 * cs - 2 - xx : xx);
+      const float w = __fmul_rn(wyv, cp->blur_taps[dx]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = fmaf(cv[(size_t)c * cs * cs + yy * cs + xx], w, acc[c]);
+    }
+  }
+  float r = acc[0], g = acc[1], b = acc[2];
+  point_effects(r, g, b, cp, flags, y, x);
+  const int64_t o = (int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)y * A.sy + (int64_t)x * A.sx;
+  if (A.normalize) {
+    r = fmaf(r, A.nscale[0], A.nbias[0]);
+    g = fmaf(g, A.nscale[1], A.nbias[1]);
+    b = fmaf(b, A.nscale[2], A.nbias[2]);
+  }
+  store_out<DstT>(A.dst, o, r);
+  store_out<DstT>(A.dst, o + A.sc, g);
+  store_out<DstT>(A.dst, o + 2 * A.sc, b);
+}
+
+// ---------------------------------------------------------------------------------
+// launcher
+// ---------------------------------------------------------------------------------
+template <typename SrcT, typename DstT>
+static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K, int aug_mode, int blur_mode) {
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int nf = K.n_frames;
+  const DevPlan& P = p->d;
+  const bool covers_source = (p->g.off_y >= 0 && p->g.off_x >= 0 && p->g.off_y + p->g.resize_h <= p->g.canvas &&
+                              p->g.off_x + p->g.resize_w <= p->g.canvas);
+  CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, (size_t)a->n_clips * sizeof(unsigned), st));
+  const int vis_rows = imin(p->g.resize_h, p->g.canvas);
+  int nbands = imax(1, imin(kMaxBands, vis_rows / 24));
+  const size_t smem = (size_t)P.src_w * 3 * sizeof(float);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(resize_general_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(nbands, nf);
+  if (!covers_source) {
+    clip_max_kernel<SrcT><<<dim3(8, nf), 256, 0, st>>>(P, K);
+    ++g_launches;
+    K.pass = 2;
+    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+    ++g_launches;
+  } else {
+    K.pass = 0;
+    const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
+    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
+    K.pass = 1;
+    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+    g_launches += 2;
+  }
+  if (aug_mode) {
+    const int cs = P.cs;
+    colour_kernel<<<dim3((K.bh * K.bw + 255) / 256, nf), 256, 0, st>>>(P, K, nbands);
+    geometry_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K, nbands);
+    g_launches += 2;
+    if (blur_mode) {
+      blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
+      ++g_launches;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NEXAR_OK;
+}
+
+extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs* a) {
+  g_launches = 0;
+  if (!p || !a) return fail(NEXAR_ERR_INVALID, "clip_transform: null argument");
+  if (a->struct_size != sizeof(NexarTransformArgs)) return fail(NEXAR_ERR_INVALID, "clip_transform: NexarTransformArgs size mismatch (ABI)");
+  if (a->n_clips <= 0 || a->frames_per_clip <= 0) return fail(NEXAR_ERR_INVALID, "clip_transform: empty batch");
+  if (!a->src || !a->frame_offsets || !a->params || !a->dst) return fail(NEXAR_ERR_INVALID, "clip_transform: null buffer");
+  if (a->dst_dtype != NEXAR_DST_F32 && a->dst_dtype != NEXAR_DST_BF16) return fail(NEXAR_ERR_INVALID, "clip_transform: bad dst_dtype");
+  const size_t need = nexar_workspace_bytes(p, a->n_clips, a->frames_per_clip);
+  if (!a->workspace || a->workspace_bytes < need) return fail(NEXAR_ERR_WORKSPACE, "clip_transform: workspace too small");
+  for (int c = 0; c < 3; ++c)
+    if (a->normalize && !(a->std[c] != 0.0f)) return fail(NEXAR_ERR_INVALID, "clip_transform: std must be non-zero");
+  const size_t esz = p->src_dtype == NEXAR_SRC_U8 ? 1 : 4;
+  if (a->src_row_stride < (int64_t)(p->g.src_w * 3 * esz)) return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
+
+  Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace);
+  KArgs K;
+  K.src = a->src;
+  K.frame_offsets = a->frame_offsets;
+  K.src_row_stride = a->src_row_stride;
+  K.params = a->params;
+  K.dst = a->dst;
+  K.sb = a->dst_stride[0];
+  K.sc = a->dst_stride[1];
+  K.st = a->dst_stride[2];
+  K.sy = a->dst_stride[3];
+  K.sx = a->dst_stride[4];
+  K.T = a->frames_per_clip;
+  K.normalize = a->normalize;
+  for (int c = 0; c < 3; ++c) {
+    const double inv = a->normalize ? 1.0 / (double)a->std[c] : 1.0;
+    K.nscale[c] = (float)inv;
+    K.nbias[c] = a->normalize ? (float)(-(double)a->mean[c] * inv) : 0.0f;
+  }
+  K.clip_max = w.clip_max;
+  K.gray_partial = w.gray_partial;
+  K.inter = w.inter;
+  K.canvas = w.canvas;
+  K.n_frames = a->n_clips * a->frames_per_clip;
+  K.bh = imin(p->g.resize_h, p->g.canvas);
+  K.bw = imin(p->g.resize_w, p->g.canvas);
+  K.pass = 0;
+  // stages no clip of the batch needs are not launched; within a launch, clips without the flag exit at once.
+  const int aug_mode = (a->any_flags & NEXAR_AUG) != 0, blur_mode = (a->any_flags & NEXAR_BLUR) != 0;
+  if (p->src_dtype == NEXAR_SRC_U8) {
+    if (a->dst_dtype == NEXAR_DST_F32) return launch_all<uint8_t, float>(p, a, K, aug_mode, blur_mode);
+    return launch_all<uint8_t, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
+  }
+  if (a->dst_dtype == NEXAR_DST_F32) return launch_all<float, float>(p, a, K, aug_mode, blur_mode);
+  return launch_all<float, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
+}
