@@ -148,8 +148,10 @@ int nexar_last_launch_count(void);
 int nexar_profile_begin(int32_t max_calls);
 int nexar_profile_end(float* ms_out, int32_t cap);
 
-/* Tuning knob for experiments: which resize kernel to use (0 = auto). */
+/* Tuning knobs for experiments: resize kernel (0 = auto, 1 = force the general fp32 kernel) and the
+ * number of row bands each frame is split into by the fast kernel (0 = auto). */
 int nexar_set_resize_kernel(int32_t variant);
+int nexar_set_fast_bands(int32_t bands);
 
 #ifdef __cplusplus
 }

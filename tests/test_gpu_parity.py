@@ -173,3 +173,27 @@ def test_full_size_properties():
     assert (oc[:, :, :, 49:174] - want).abs().max() <= 1e-5
     # idempotence / determinism
     assert torch.equal(out, tf.forward_batch(clips, params=recs))
+
+
+@pytest.mark.parametrize("name", ["val_720p_noise", "train_720p_dashcam", "custom_720p_dashcam", "val_1080p_noise",
+                                  "val_720p_320", "val_small", "val_portrait", "train_portrait_flip",
+                                  "custom_small_s0", "allfx_small_s1"])
+@pytest.mark.parametrize("bands", [0, 1, 3, 7])
+def test_fast_and_general_resize_kernels_agree(name, bands):
+    """The fixed-point input-stationary kernel and the general fp32 kernel both meet the gate, for any banding."""
+    from vision_collision_detection_b200 import _lib
+    c = load_case(name)
+    tol = TOL_AFTER if c["cfg"].normalize else TOL_BEFORE
+    L = _lib.lib()
+    try:
+        L.nexar_set_resize_kernel(1)
+        general = _run(_tf(c["kwargs"]), c["clip"], c["params"])
+        L.nexar_set_resize_kernel(0)
+        L.nexar_set_fast_bands(bands)
+        fast = _run(_tf(c["kwargs"]), c["clip"], c["params"])
+    finally:
+        L.nexar_set_resize_kernel(0)
+        L.nexar_set_fast_bands(0)
+    assert np.abs(general - c["out"]).max() <= tol
+    assert np.abs(fast - c["out"]).max() <= tol
+    assert np.abs(fast - general).max() <= 2.5e-4      # fixed-point budget: < 3e-5 of full scale, /0.225

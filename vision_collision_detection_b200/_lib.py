@@ -114,6 +114,7 @@ def lib():
     L.nexar_clip_transform.argtypes = [C.c_void_p, C.POINTER(TransformArgs)]
     L.nexar_last_launch_count.restype = C.c_int
     L.nexar_set_resize_kernel.argtypes = [C.c_int32]
+    L.nexar_set_fast_bands.argtypes = [C.c_int32]
     L.nexar_profile_begin.argtypes = [C.c_int32]
     L.nexar_profile_end.argtypes = [C.c_void_p, C.c_int32]
     if L.nexar_abi_version() != NEXAR_ABI_VERSION:

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <type_traits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -26,10 +27,13 @@
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-static int g_resize_variant = 0;
+static int g_resize_variant = 0;  // 0 auto, 1 force the general kernel
+static int g_fast_bands = 0;      // 0 auto
 
 static std::vector<cudaEvent_t> g_prof_ev;
 static int g_prof_n = 0;
+
+static inline int imin_host(int a, int b) { return a < b ? a : b; }
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -53,6 +57,12 @@ struct DevPlan {
   const int* xstart;
   const int* xcount;
   const float* xwt;
+  // fast (fixed-point, input-stationary) resize tables; pairs == nullptr when not applicable
+  const uint4* pairs;      // [n_pairs] {w slot0, w slot1, w slot2 (u16x2: row 2p | row 2p+1 << 16), emit (count | first_row << 2)}
+  int n_pairs, shift;      // weights are round(w * 2^shift), every row sums to exactly 2^shift
+  const int* xstart_al;    // [rw] even-aligned first tap
+  const float* xwt_al;     // [rw][kx_al] taps shifted to the aligned start
+  int kx_al;
 };
 
 struct NexarPlan {
@@ -62,7 +72,71 @@ struct NexarPlan {
   void* dev_tables;
   std::vector<int> ystart, ycount, xstart, xcount;
   std::vector<float> ywt, xwt;
+  bool fast_ok = false;
+  std::vector<uint4> pairs;
+  std::vector<int> xstart_al;
+  std::vector<float> xwt_al;
 };
+
+// Fixed-point vertical taps for the input-stationary kernel: three rotating accumulator slots
+// (out row i lives in slot i % 3) fed with row PAIRS through dp2a.  Returns false when the geometry
+// does not fit the scheme (up-scaling, too many overlapping rows, tap table too wide).
+static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
+  const NexarGeometry& g = p->g;
+  if (p->src_dtype != NEXAR_SRC_U8) return false;
+  if ((g.src_w * 3) % 16 != 0 || g.src_w * 3 / 16 > 384) return false;
+  if (g.src_h < g.resize_h || g.src_w < g.resize_w) return false;  // down-scale only
+  if (imin_host(g.resize_w, g.canvas) > 384) return false;
+  kx_al = kx + 1;
+  kx_al = kx_al <= 10 ? 10 : kx_al <= 14 ? 14 : kx_al <= 20 ? 20 : 0;
+  if (!kx_al) return false;
+  float wmax = 0.f;
+  for (float w : p->ywt) wmax = w > wmax ? w : wmax;
+  if (!(wmax > 0.f)) return false;
+  shift = 18;
+  while (shift > 8 && std::ldexp((double)wmax, shift) > 65535.0) --shift;
+  if (std::ldexp((double)wmax, shift) > 65535.0) return false;
+  const int n_pairs = (g.src_h + 1) / 2;
+  p->pairs.assign(n_pairs, make_uint4(0, 0, 0, 0));
+  int last_pl[3] = {-1, -1, -1};
+  int prev_pl = -1;
+  for (int i = 0; i < g.resize_h; ++i) {
+    const int ys = p->ystart[i], yc = p->ycount[i];
+    if (yc <= 0) return false;
+    const float* w = &p->ywt[(size_t)i * ky];
+    std::vector<long> q(yc);
+    long sum = 0;
+    int arg = 0;
+    for (int k = 0; k < yc; ++k) {
+      q[k] = std::lrint(std::ldexp((double)w[k], shift));
+      sum += q[k];
+      if (q[k] > q[arg]) arg = k;
+    }
+    q[arg] += (1L << shift) - sum;  // rows sum to exactly 2^shift: constant images stay constant
+    if (q[arg] < 0 || q[arg] > 65535) return false;
+    const int slot = i % 3, pf = ys / 2, pl = (ys + yc - 1) / 2;
+    if (pf <= last_pl[slot] || pl < prev_pl) return false;
+    last_pl[slot] = pl;
+    prev_pl = pl;
+    for (int k = 0; k < yc; ++k) {
+      const int y = ys + k;
+      unsigned* e = &p->pairs[y / 2].x;
+      e[slot] |= (unsigned)q[k] << (16 * (y & 1));
+    }
+    unsigned& em = p->pairs[pl].w;
+    if ((em & 3u) == 0) em = (unsigned)i << 2;
+    if ((em & 3u) == 3u) return false;
+    em += 1;
+  }
+  p->xstart_al.assign(g.resize_w, 0);
+  p->xwt_al.assign((size_t)g.resize_w * kx_al, 0.f);
+  for (int j = 0; j < g.resize_w; ++j) {
+    const int xs = p->xstart[j], al = xs & ~1, sh = xs - al;
+    p->xstart_al[j] = al;
+    for (int k = 0; k < p->xcount[j]; ++k) p->xwt_al[(size_t)j * kx_al + k + sh] = p->xwt[(size_t)j * kx + k];
+  }
+  return true;
+}
 
 // ATen UpSampleKernel.cpp _compute_indices_min_size_weights_aa, float opmath.
 static void aa_taps_host(int in_size, int out_size, std::vector<int>& start, std::vector<int>& count,
@@ -105,6 +179,10 @@ extern "C" const char* nexar_last_error(void) { return g_err.c_str(); }
 extern "C" int nexar_last_launch_count(void) { return g_launches; }
 extern "C" int nexar_set_resize_kernel(int32_t v) {
   g_resize_variant = v;
+  return NEXAR_OK;
+}
+extern "C" int nexar_set_fast_bands(int32_t n) {
+  g_fast_bands = n;
   return NEXAR_OK;
 }
 
@@ -203,31 +281,38 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   int ky = 0, kx = 0;
   aa_taps_host(g->src_h, g->resize_h, p->ystart, p->ycount, p->ywt, ky);
   aa_taps_host(g->src_w, g->resize_w, p->xstart, p->xcount, p->xwt, kx);
-  const size_t ni = (size_t)(g->resize_h + g->resize_w) * 2 * sizeof(int);
-  const size_t nf = ((size_t)g->resize_h * ky + (size_t)g->resize_w * kx) * sizeof(float);
+  int shift = 0, kx_al = 0;
+  p->fast_ok = build_fast_tables(p, ky, kx, shift, kx_al);
+  // one device allocation: [pairs (16B aligned)] [ints] [floats]
+  const size_t n_pairs_b = p->fast_ok ? p->pairs.size() * sizeof(uint4) : 0;
+  const size_t ni = ((size_t)(g->resize_h + g->resize_w) * 2 + (p->fast_ok ? g->resize_w : 0)) * sizeof(int);
+  const size_t nf = ((size_t)g->resize_h * ky + (size_t)g->resize_w * kx + (p->fast_ok ? p->xwt_al.size() : 0)) * sizeof(float);
   p->dev_tables = nullptr;
-  cudaError_t e = cudaMalloc(&p->dev_tables, ni + nf);
+  cudaError_t e = cudaMalloc(&p->dev_tables, n_pairs_b + ni + nf);
   if (e != cudaSuccess) {
     delete p;
     return fail(NEXAR_ERR_CUDA, std::string("plan_create: cudaMalloc: ") + cudaGetErrorString(e));
   }
-  std::vector<char> host(ni + nf);
-  int* hi = (int*)host.data();
+  std::vector<char> host(n_pairs_b + ni + nf);
+  if (n_pairs_b) memcpy(host.data(), p->pairs.data(), n_pairs_b);
+  int* hi = (int*)(host.data() + n_pairs_b);
   memcpy(hi, p->ystart.data(), g->resize_h * sizeof(int));
   memcpy(hi + g->resize_h, p->ycount.data(), g->resize_h * sizeof(int));
   memcpy(hi + 2 * g->resize_h, p->xstart.data(), g->resize_w * sizeof(int));
   memcpy(hi + 2 * g->resize_h + g->resize_w, p->xcount.data(), g->resize_w * sizeof(int));
-  float* hf = (float*)(host.data() + ni);
+  if (p->fast_ok) memcpy(hi + 2 * g->resize_h + 2 * g->resize_w, p->xstart_al.data(), g->resize_w * sizeof(int));
+  float* hf = (float*)(host.data() + n_pairs_b + ni);
   memcpy(hf, p->ywt.data(), p->ywt.size() * sizeof(float));
   memcpy(hf + p->ywt.size(), p->xwt.data(), p->xwt.size() * sizeof(float));
-  e = cudaMemcpy(p->dev_tables, host.data(), ni + nf, cudaMemcpyHostToDevice);
+  if (p->fast_ok) memcpy(hf + p->ywt.size() + p->xwt.size(), p->xwt_al.data(), p->xwt_al.size() * sizeof(float));
+  e = cudaMemcpy(p->dev_tables, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(p->dev_tables);
     delete p;
     return fail(NEXAR_ERR_CUDA, std::string("plan_create: cudaMemcpy: ") + cudaGetErrorString(e));
   }
-  int* di = (int*)p->dev_tables;
-  float* df = (float*)((char*)p->dev_tables + ni);
+  int* di = (int*)((char*)p->dev_tables + n_pairs_b);
+  float* df = (float*)((char*)p->dev_tables + n_pairs_b + ni);
   DevPlan& d = p->d;
   d.src_h = g->src_h;
   d.src_w = g->src_w;
@@ -244,6 +329,12 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   d.xcount = di + 2 * g->resize_h + g->resize_w;
   d.ywt = df;
   d.xwt = df + p->ywt.size();
+  d.pairs = p->fast_ok ? (const uint4*)p->dev_tables : nullptr;
+  d.n_pairs = (int)p->pairs.size();
+  d.shift = shift;
+  d.xstart_al = p->fast_ok ? di + 2 * g->resize_h + 2 * g->resize_w : nullptr;
+  d.xwt_al = p->fast_ok ? df + p->ywt.size() + p->xwt.size() : nullptr;
+  d.kx_al = kx_al;
   *out = p;
   return NEXAR_OK;
 }
@@ -270,7 +361,7 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 static const int kMaxBands = 16;
 
 struct Workspace {
-  unsigned* clip_max;   // [n_clips] order-preserving uint image of the float maximum
+  unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
   float* gray_partial;  // [2][n_frames][kMaxBands]
   float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
@@ -321,14 +412,6 @@ struct KArgs {
   int bh, bw;  // allocation dims of one intermediate frame
   int pass;    // 0: assume /255 and record max; 1: redo clips whose max <= 1 without scaling; 2: max already known
 };
-
-__device__ __forceinline__ unsigned ordered_bits(float f) {
-  unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ordered_to_float(unsigned u) {
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
 
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 // tv rgb_to_grayscale: (0.2989 r + 0.587 g) + 0.114 b, every product rounded (no fma contraction)
@@ -406,7 +489,7 @@ __global__ void clip_max_kernel(DevPlan P, KArgs A) {
     for (int e = threadIdx.x; e < n; e += blockDim.x) m = fmaxf(m, (float)row[e]);
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(&A.clip_max[clip], ordered_bits(m));
+  if ((threadIdx.x & 31) == 0 && m > 1.0f) atomicOr(&A.clip_max[clip], 1u);
 }
 
 // ---------------------------------------------------------------------------------
@@ -426,7 +509,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
   if (A.pass == 0) {
     scale = 1.0f / 255.0f;
   } else {
-    const bool big = ordered_to_float(A.clip_max[clip]) > 1.0f;
+    const bool big = A.clip_max[clip] != 0u;
     if (A.pass == 1 && big) return;
     scale = big ? 1.0f / 255.0f : 1.0f;
   }
@@ -511,11 +594,232 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 
   if (A.pass == 0) {
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&A.clip_max[clip], ordered_bits(vmax));
+    if ((threadIdx.x & 31) == 0 && vmax > 1.0f) atomicOr(&A.clip_max[clip], 1u);
   }
   if (aug) {
     const float s = block_sum(gsum, red);
     if (threadIdx.x == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------
+// K1 (fast variant): input-stationary fixed-point vertical pass + fp32 horizontal pass.
+//
+// Down-scaling uint8 frames whose rows are a multiple of 16 bytes.  A CTA owns one band of
+// resized rows of one frame and streams the source rows it needs exactly once, two rows per
+// step: every thread keeps one 16-byte column chunk (128-bit coalesced loads, prefetched
+// PF pairs ahead in registers), interleaves the two rows' bytes with PRMT and feeds them to
+// dp2a against the 16-bit fixed-point taps of the (at most three) output rows alive at that
+// height (rotating accumulator slots, out row i in slot i % 3).  A finished row is rounded
+// to 15-bit fixed point (value*128), staged in shared memory (double buffered: one
+// __syncthreads per output row) and resampled horizontally in fp32, one output pixel per
+// thread with its taps in registers.  The uint16 -> float conversion is a single PRMT that
+// builds the float 2^15 + v; the constant 2^15 * sum(w) is removed after the tap loop.
+// Worst-case error of the fixed-point steps: 2^-19 * 255 * taps/2 (weights) + 2^-8 (staging)
+// in 0..255 units, i.e. < 3e-5 of full scale (gate: 1/255 before, 1e-3 after normalisation).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float magic_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4105)); }
+__device__ __forceinline__ float magic_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4325)); }
+
+template <int KX, int NT, int MINB, typename DstT>
+__global__ void __launch_bounds__(NT, MINB) resize_fast_kernel(DevPlan P, KArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[32];
+  constexpr int PF = 4;  // row pairs in flight per thread
+  const int tid = threadIdx.x;
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const int t = frame - clip * A.T;
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  float scale;
+  if (A.pass == 0) {
+    scale = 1.0f / 255.0f;
+  } else {
+    const bool big = A.clip_max[clip] != 0u;
+    if (A.pass == 1 && big) return;
+    scale = big ? 1.0f / 255.0f : 1.0f;
+  }
+  const bool flip = flags & NEXAR_FLIP, aug = flags & NEXAR_AUG;
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flip);
+  const int nb = gridDim.x, band = blockIdx.x;
+  const int per = (B.i_hi - B.i_lo + nb - 1) / nb;
+  const int i0 = min(B.i_hi, B.i_lo + band * per), i1 = min(B.i_hi, i0 + per);
+  const int W3 = P.src_w * 3;
+  const int nchunks = W3 >> 4;
+  const int vstride = (W3 + KX * 3 + 15) & ~7;  // uint16 elements per staging buffer (16-byte multiple)
+  unsigned short* vb = (unsigned short*)smem_raw;
+  for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
+
+  const float bright = cp->brightness;
+  float nsc[3], nbi[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    nsc[c] = A.normalize ? A.nscale[c] : 1.0f;
+    nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
+  }
+  const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
+
+  // horizontal taps of this thread's output pixel
+  const int nj = B.j_hi - B.j_lo;
+  const bool hth = tid < nj;
+  const int j = B.j_lo + (hth ? tid : 0);
+  float wx[KX];
+#pragma unroll
+  for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
+  float hbias = 0.0f;
+#pragma unroll
+  for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
+  const int hword = (P.xstart_al[j] * 3) >> 1;  // 32-bit word offset of the first tap in the staging row
+  int xo = j + B.ox;
+  if (flip) xo = P.cs - 1 - xo;
+  const float post = scale * (1.0f / 128.0f);
+
+  const bool vth = tid < nchunks;
+  const int sh = P.shift - 7;
+  const unsigned rnd = 1u << (sh - 1);
+  unsigned acc0[16], acc1[16], acc2[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = acc2[q] = rnd;
+  unsigned orv = 0u;
+  float gsum = 0.0f;
+  int buf = 0;
+
+  if (i0 < i1) {
+    const int p0 = P.ystart[i0] >> 1;
+    const int p1 = ((P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1) + 1;
+    const char* fbase = (const char*)A.src + A.frame_offsets[frame] + (size_t)tid * 16;
+    const int64_t rs = A.src_row_stride;
+    const int H = P.src_h;
+    uint4 ra[PF], rb[PF];
+    auto load_pair = [&](int p, uint4& a, uint4& b) {
+      a = make_uint4(0, 0, 0, 0);
+      b = a;
+      if (vth && p < p1) {
+        a = __ldcs((const uint4*)(fbase + (int64_t)(2 * p) * rs));
+        if (2 * p + 1 < H) b = __ldcs((const uint4*)(fbase + (int64_t)(2 * p + 1) * rs));
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) load_pair(p0 + u, ra[u], rb[u]);
+
+    auto accumulate = [&](unsigned (&acc)[16], unsigned w, const unsigned (&lo)[4], const unsigned (&hi)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[4 * q + 0] = __dp2a_lo(w, lo[q], acc[4 * q + 0]);
+        acc[4 * q + 1] = __dp2a_hi(w, lo[q], acc[4 * q + 1]);
+        acc[4 * q + 2] = __dp2a_lo(w, hi[q], acc[4 * q + 2]);
+        acc[4 * q + 3] = __dp2a_hi(w, hi[q], acc[4 * q + 3]);
+      }
+    };
+    auto stage = [&](unsigned (&acc)[16], unsigned short* dst) {
+      unsigned w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        w[q] = (acc[2 * q] >> sh) | ((acc[2 * q + 1] >> sh) << 16);
+        acc[2 * q] = acc[2 * q + 1] = rnd;
+      }
+      uint4* d = (uint4*)(dst + tid * 16);
+      d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    };
+    auto reset = [&](unsigned (&acc)[16]) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = rnd;
+    };
+
+    for (int pb = p0; pb < p1; pb += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int p = pb + u;
+        if (p < p1) {
+          const uint4 a = ra[u], b = rb[u];
+          load_pair(p + PF, ra[u], rb[u]);
+          const uint4 e = __ldg(P.pairs + p);
+          if (vth) {
+            orv |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | b.w);
+            unsigned lo[4], hi[4];
+            lo[0] = __byte_perm(a.x, b.x, 0x5140); hi[0] = __byte_perm(a.x, b.x, 0x7362);
+            lo[1] = __byte_perm(a.y, b.y, 0x5140); hi[1] = __byte_perm(a.y, b.y, 0x7362);
+            lo[2] = __byte_perm(a.z, b.z, 0x5140); hi[2] = __byte_perm(a.z, b.z, 0x7362);
+            lo[3] = __byte_perm(a.w, b.w, 0x5140); hi[3] = __byte_perm(a.w, b.w, 0x7362);
+            if (e.x) accumulate(acc0, e.x, lo, hi);
+            if (e.y) accumulate(acc1, e.y, lo, hi);
+            if (e.z) accumulate(acc2, e.z, lo, hi);
+          }
+          int row = (int)(e.w >> 2);
+          for (int n = (int)(e.w & 3u); n > 0; --n, ++row) {
+            const int s = row % 3;
+            if (row < i0 || row >= i1) {  // a neighbour band's row: drop it
+              if (vth) {
+                if (s == 0) reset(acc0); else if (s == 1) reset(acc1); else reset(acc2);
+              }
+              continue;
+            }
+            unsigned short* vcur = vb + buf * vstride;
+            if (vth) {
+              if (s == 0) stage(acc0, vcur); else if (s == 1) stage(acc1, vcur); else stage(acc2, vcur);
+            }
+            __syncthreads();
+            if (hth) {
+              const unsigned* src = (const unsigned*)vcur + hword;
+              float r = 0.0f, g = 0.0f, bl = 0.0f;
+#pragma unroll
+              for (int k = 0; k < KX; k += 2) {
+                const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2];
+                r = fmaf(wx[k], magic_lo(w0), r);
+                g = fmaf(wx[k], magic_hi(w0), g);
+                bl = fmaf(wx[k], magic_lo(w1), bl);
+                r = fmaf(wx[k + 1], magic_hi(w1), r);
+                g = fmaf(wx[k + 1], magic_lo(w2), g);
+                bl = fmaf(wx[k + 1], magic_hi(w2), bl);
+              }
+              r = (r - hbias) * post;
+              g = (g - hbias) * post;
+              bl = (bl - hbias) * post;
+              const int y = row + B.oy;
+              if (aug) {
+                r = clamp01(__fmul_rn(bright, r));
+                g = clamp01(__fmul_rn(bright, g));
+                bl = clamp01(__fmul_rn(bright, bl));
+                gsum += gray_of(r, g, bl);
+                A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (xo - B.bx0)] = make_float4(r, g, bl, 0.0f);
+              } else {
+                const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)xo * A.sx;
+                store_out<DstT>(A.dst, o, fmaf(r, nsc[0], nbi[0]));
+                store_out<DstT>(A.dst, o + A.sc, fmaf(g, nsc[1], nbi[1]));
+                store_out<DstT>(A.dst, o + 2 * A.sc, fmaf(bl, nsc[2], nbi[2]));
+              }
+            }
+            buf ^= 1;
+          }
+        }
+      }
+    }
+  }
+
+  if (!aug) {
+    const int Y0 = band == 0 ? 0 : i0 + B.oy;
+    const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
+    const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;
+    for (int y = Y0; y < Y1; ++y) {
+      const bool content_row = (y >= cy0 && y < cy1);
+      for (int x = tid; x < P.cs; x += NT) {
+        if (content_row && x >= B.bx0 && x < B.bx1) continue;
+        const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+      }
+    }
+  }
+  if (A.pass == 0) {
+    const bool big = (orv & 0xFEFEFEFEu) != 0u;
+    if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
+  }
+  if (aug) {
+    const float s = block_sum(gsum, red);
+    if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
 }
 
@@ -585,7 +889,7 @@ __global__ void __launch_bounds__(256) colour_kernel(DevPlan P, KArgs A, int nba
   const int clip = frame / A.T;
   const NexarClipParams* cp = A.params + clip;
   if (!(cp->flags & NEXAR_AUG)) return;
-  const int slot = ordered_to_float(A.clip_max[clip]) > 1.0f ? 0 : 1;
+  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
   const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, cp->flags & NEXAR_FLIP);
   const int h = B.by1 - B.by0, w = B.bx1 - B.bx0;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -649,7 +953,7 @@ __global__ void __launch_bounds__(256) geometry_kernel(DevPlan P, KArgs A, int n
   const NexarClipParams* cp = A.params + clip;
   const unsigned flags = cp->flags;
   if (!(flags & NEXAR_AUG)) return;
-  const int slot = ordered_to_float(A.clip_max[clip]) > 1.0f ? 0 : 1;
+  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
   const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flags & NEXAR_FLIP);
   const int cs = P.cs;
   if (threadIdx.x == 0) {
@@ -786,26 +1090,51 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
                               p->g.off_x + p->g.resize_w <= p->g.canvas);
   CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, (size_t)a->n_clips * sizeof(unsigned), st));
   const int vis_rows = imin(p->g.resize_h, p->g.canvas);
-  int nbands = imax(1, imin(kMaxBands, vis_rows / 24));
-  const size_t smem = (size_t)P.src_w * 3 * sizeof(float);
-  if (smem > 48 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(resize_general_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(nbands, nf);
-  if (!covers_source) {
-    clip_max_kernel<SrcT><<<dim3(8, nf), 256, 0, st>>>(P, K);
-    ++g_launches;
-    K.pass = 2;
-    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
-    ++g_launches;
+  const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
+  int nbands;
+  const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
+                        a->src_row_stride % 16 == 0 && ((uintptr_t)a->src % 16) == 0;
+  if (use_fast) {
+    nbands = g_fast_bands > 0 ? imin(g_fast_bands, kMaxBands) : imax(1, imin(kMaxBands, (vis_rows + 24) / 25));
+    nbands = imax(1, imin(nbands, vis_rows));
+    const int need_threads = imax(P.src_w * 3 / 16, imin(P.rw, P.cs));
+    const int kx = P.kx_al;
+    const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
+    dim3 grid(nbands, nf);
+    for (int pass = 0; pass < 2; ++pass) {
+      K.pass = pass;
+      if (pass == 0 && prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K)
+      if (need_threads <= 256) {
+        if (kx == 10) NEXAR_FAST(10, 256, 2); else if (kx == 14) NEXAR_FAST(14, 256, 2); else NEXAR_FAST(20, 256, 2);
+      } else {
+        if (kx == 10) NEXAR_FAST(10, 384, 1); else if (kx == 14) NEXAR_FAST(14, 384, 1); else NEXAR_FAST(20, 384, 1);
+      }
+#undef NEXAR_FAST
+      if (pass == 0 && prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
+      ++g_launches;
+    }
   } else {
-    K.pass = 0;
-    const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
-    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
-    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
-    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
-    K.pass = 1;
-    resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
-    g_launches += 2;
+    nbands = imax(1, imin(kMaxBands, vis_rows / 24));
+    const size_t smem = (size_t)P.src_w * 3 * sizeof(float);
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(resize_general_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nbands, nf);
+    if (!covers_source) {
+      clip_max_kernel<SrcT><<<dim3(8, nf), 256, 0, st>>>(P, K);
+      ++g_launches;
+      K.pass = 2;
+      resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+      ++g_launches;
+    } else {
+      K.pass = 0;
+      if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+      resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+      if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
+      K.pass = 1;
+      resize_general_kernel<SrcT, DstT><<<grid, 256, smem, st>>>(P, K);
+      g_launches += 2;
+    }
   }
   if (aug_mode) {
     const int cs = P.cs;
