@@ -195,6 +195,9 @@ def main():
     out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
     tf = create_video_transforms(**KW[args.mode], crop_size=cs, out_dtype=out_dtype)
     eng = get_engine(dev)
+    if os.environ.get("NEXAR_FAST_BANDS"):
+        from vision_collision_detection_b200 import _lib as _l
+        _l.lib().nexar_set_fast_bands(int(os.environ["NEXAR_FAST_BANDS"]))
 
     # synthetic device-resident shard (1.4 GB for cfg2: larger than the 126 MB L2, so every step streams from HBM)
     clips = torch.stack([make_clip_torch(t, h, w, seed=rank * 1000 + i, kind="dashcam", device=dev) for i in range(b)])

@@ -14,7 +14,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT_DIR = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libnexar_clip_b200.so")
+LIB_PATH = os.environ.get("NEXAR_LIB") or os.path.join(PKG_DIR, "libnexar_clip_b200.so")  # NEXAR_LIB: experiment builds
 SOURCES = [os.path.join(PKG_DIR, "csrc", "clip_transform.cu")]
 HEADERS = [os.path.join(ROOT_DIR, "include", "nexar_clip_transform.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

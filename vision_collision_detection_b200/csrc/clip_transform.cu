@@ -78,14 +78,19 @@ struct NexarPlan {
   std::vector<float> xwt_al;
 };
 
-// Fixed-point vertical taps for the input-stationary kernel: three rotating accumulator slots
-// (out row i lives in slot i % 3) fed with row PAIRS through dp2a.  Returns false when the geometry
-// does not fit the scheme (up-scaling, too many overlapping rows, tap table too wide).
+// Fixed-point vertical taps for the input-stationary kernel.  The triangle filter of a >= 2x
+// down-scale keeps at most two output rows alive at any source row (ymin[i+2] >= ymax[i]), so two
+// rotating accumulator slots suffice (out row i lives in slot i % 2).  The kernel consumes source rows
+// in PAIRS through dp2a; table entry p = {w slot0, w slot1, w post, emit} with w = u16x2 (row 2p | row
+// 2p+1 << 16), emit = 0 or (1 | slot << 1 | out_row << 2) when an output row's last tap lies in this
+// pair, and "w post" the first tap of the NEXT row of that slot when it falls in the same pair (it is
+// accumulated after the finished row has been flushed).  Returns false when the geometry does not fit.
+static const int kMaxPairs = 1024;
 static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
   const NexarGeometry& g = p->g;
   if (p->src_dtype != NEXAR_SRC_U8) return false;
   if ((g.src_w * 3) % 16 != 0 || g.src_w * 3 / 16 > 384) return false;
-  if (g.src_h < g.resize_h || g.src_w < g.resize_w) return false;  // down-scale only
+  if (g.src_h < 2 * g.resize_h || g.src_w < g.resize_w) return false;  // vertical down-scale by >= 2
   if (imin_host(g.resize_w, g.canvas) > 384) return false;
   kx_al = kx + 1;
   kx_al = kx_al <= 10 ? 10 : kx_al <= 14 ? 14 : kx_al <= 20 ? 20 : 0;
@@ -97,12 +102,13 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
   while (shift > 8 && std::ldexp((double)wmax, shift) > 65535.0) --shift;
   if (std::ldexp((double)wmax, shift) > 65535.0) return false;
   const int n_pairs = (g.src_h + 1) / 2;
+  if (n_pairs > kMaxPairs) return false;
   p->pairs.assign(n_pairs, make_uint4(0, 0, 0, 0));
-  int last_pl[3] = {-1, -1, -1};
-  int prev_pl = -1;
   for (int i = 0; i < g.resize_h; ++i) {
     const int ys = p->ystart[i], yc = p->ycount[i];
     if (yc <= 0) return false;
+    if (i + 2 < g.resize_h && p->ystart[i + 2] < ys + yc) return false;  // three rows alive at once
+    if (i + 1 < g.resize_h && p->ystart[i + 1] + p->ycount[i + 1] <= ys + yc) return false;  // must finish in order
     const float* w = &p->ywt[(size_t)i * ky];
     std::vector<long> q(yc);
     long sum = 0;
@@ -114,19 +120,22 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
     }
     q[arg] += (1L << shift) - sum;  // rows sum to exactly 2^shift: constant images stay constant
     if (q[arg] < 0 || q[arg] > 65535) return false;
-    const int slot = i % 3, pf = ys / 2, pl = (ys + yc - 1) / 2;
-    if (pf <= last_pl[slot] || pl < prev_pl) return false;
-    last_pl[slot] = pl;
-    prev_pl = pl;
+    const int slot = i % 2;
+    const int prev_last = i >= 2 ? p->ystart[i - 2] + p->ycount[i - 2] - 1 : -1;  // last tap of the slot's previous row
     for (int k = 0; k < yc; ++k) {
       const int y = ys + k;
-      unsigned* e = &p->pairs[y / 2].x;
-      e[slot] |= (unsigned)q[k] << (16 * (y & 1));
+      uint4& e = p->pairs[y / 2];
+      if (prev_last >= 0 && prev_last / 2 == y / 2) {
+        if (!(y & 1) || e.z) return false;
+        e.z = (unsigned)q[k] << 16;
+      } else {
+        unsigned& ws = slot ? e.y : e.x;
+        ws |= (unsigned)q[k] << (16 * (y & 1));
+      }
     }
-    unsigned& em = p->pairs[pl].w;
-    if ((em & 3u) == 0) em = (unsigned)i << 2;
-    if ((em & 3u) == 3u) return false;
-    em += 1;
+    unsigned& em = p->pairs[(ys + yc - 1) / 2].w;
+    if (em) return false;  // one flush per pair
+    em = 1u | ((unsigned)slot << 1) | ((unsigned)i << 2);
   }
   p->xstart_al.assign(g.resize_w, 0);
   p->xwt_al.assign((size_t)g.resize_w * kx_al, 0.f);
@@ -359,6 +368,8 @@ static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
 static const int kMaxBands = 16;
+struct PairTable;
+
 
 struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
@@ -606,27 +617,49 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 // ---------------------------------------------------------------------------------
 // K1 (fast variant): input-stationary fixed-point vertical pass + fp32 horizontal pass.
 //
-// Down-scaling uint8 frames whose rows are a multiple of 16 bytes.  A CTA owns one band of
-// resized rows of one frame and streams the source rows it needs exactly once, two rows per
-// step: every thread keeps one 16-byte column chunk (128-bit coalesced loads, prefetched
-// PF pairs ahead in registers), interleaves the two rows' bytes with PRMT and feeds them to
-// dp2a against the 16-bit fixed-point taps of the (at most three) output rows alive at that
-// height (rotating accumulator slots, out row i in slot i % 3).  A finished row is rounded
-// to 15-bit fixed point (value*128), staged in shared memory (double buffered: one
-// __syncthreads per output row) and resampled horizontally in fp32, one output pixel per
-// thread with its taps in registers.  The uint16 -> float conversion is a single PRMT that
-// builds the float 2^15 + v; the constant 2^15 * sum(w) is removed after the tap loop.
-// Worst-case error of the fixed-point steps: 2^-19 * 255 * taps/2 (weights) + 2^-8 (staging)
-// in 0..255 units, i.e. < 3e-5 of full scale (gate: 1/255 before, 1e-3 after normalisation).
+// Down-scaling (>= 2x vertically) uint8 frames whose rows are a multiple of 16 bytes.  A CTA owns
+// one band of resized rows of one frame and streams the source rows it needs exactly once, two rows
+// per step.  Every thread keeps one 16-byte column chunk: 128-bit coalesced streaming loads, PF
+// pairs ahead in registers, with one elected thread pushing the rows LOOKAHEAD pairs ahead into L2
+// through the bulk-copy engine (cp.async.bulk.prefetch.L2).  The two rows' bytes are interleaved
+// with PRMT and fed to dp2a against the 16-bit fixed-point taps of the (at most two) output rows
+// alive at that height.  The tap table lives in the kernel parameters (constant bank), so the
+// per-pair control flow is uniform.  A finished row is rounded to 15-bit fixed point (value*128),
+// staged in shared memory (double buffered: one __syncthreads per output row) and resampled
+// horizontally in fp32, one output pixel per thread with its taps in registers.  The uint16 ->
+// float conversion is a single PRMT that builds the float 2^15 + v; the constant 2^15 * sum(w) is
+// removed after the tap loop.  Worst-case error of the fixed-point steps: 2^-19 * 255 * taps/2
+// (weights) + 2^-8 (staging) in 0..255 units, i.e. < 3e-5 of full scale (gate: 1/255 before,
+// 1e-3 after normalisation).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ float magic_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4105)); }
 __device__ __forceinline__ float magic_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4325)); }
 
+struct PairTable {
+  uint4 e[kMaxPairs];
+};
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+#ifndef NEXAR_PF
+#define NEXAR_PF 2
+#endif
+#ifndef NEXAR_MINB
+#define NEXAR_MINB 3
+#endif
+#ifndef NEXAR_LOOKAHEAD
+#define NEXAR_LOOKAHEAD 12
+#endif
+
 template <int KX, int NT, int MINB, typename DstT>
-__global__ void __launch_bounds__(NT, MINB) resize_fast_kernel(DevPlan P, KArgs A) {
+__global__ void __launch_bounds__(NT, MINB)
+resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, const __grid_constant__ PairTable TB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
-  constexpr int PF = 4;  // row pairs in flight per thread
+  constexpr int PF = NEXAR_PF;         // row pairs in flight per thread (registers)
+  constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine
   const int tid = threadIdx.x;
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
@@ -652,157 +685,171 @@ __global__ void __launch_bounds__(NT, MINB) resize_fast_kernel(DevPlan P, KArgs 
   unsigned short* vb = (unsigned short*)smem_raw;
   for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
 
-  const float bright = cp->brightness;
-  float nsc[3], nbi[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    nsc[c] = A.normalize ? A.nscale[c] : 1.0f;
-    nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
-  }
   const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
-
-  // horizontal taps of this thread's output pixel
-  const int nj = B.j_hi - B.j_lo;
-  const bool hth = tid < nj;
-  const int j = B.j_lo + (hth ? tid : 0);
-  float wx[KX];
-#pragma unroll
-  for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
-  float hbias = 0.0f;
-#pragma unroll
-  for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
-  const int hword = (P.xstart_al[j] * 3) >> 1;  // 32-bit word offset of the first tap in the staging row
-  int xo = j + B.ox;
-  if (flip) xo = P.cs - 1 - xo;
-  const float post = scale * (1.0f / 128.0f);
-
-  const bool vth = tid < nchunks;
-  const int sh = P.shift - 7;
-  const unsigned rnd = 1u << (sh - 1);
-  unsigned acc0[16], acc1[16], acc2[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = acc2[q] = rnd;
-  unsigned orv = 0u;
   float gsum = 0.0f;
-  int buf = 0;
+  unsigned orv = 0u;
 
   if (i0 < i1) {
+    // ---- horizontal taps of this thread's output pixel (registers) ----
+    const int nj = B.j_hi - B.j_lo;
+    const bool hth = tid < nj;
+    const int j = B.j_lo + (hth ? tid : 0);
+    float wx[KX];
+#pragma unroll
+    for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
+    float hbias = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
+    const int hword = (P.xstart_al[j] * 3) >> 1;  // 32-bit word offset of the first tap in the staging row
+    int xo = j + B.ox;
+    if (flip) xo = P.cs - 1 - xo;
+    const float post = scale * (1.0f / 128.0f);
+
+    // ---- vertical pass state ----
+    const int sh = P.shift - 7;
+    const unsigned rnd = 1u << (sh - 1);
+    unsigned acc0[16], acc1[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = rnd;
+    int buf = 0;
     const int p0 = P.ystart[i0] >> 1;
-    const int p1 = ((P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1) + 1;
-    const char* fbase = (const char*)A.src + A.frame_offsets[frame] + (size_t)tid * 16;
+    const int plast = (P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1;  // inclusive
+    const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
+    const bool vstore = tid < nchunks;
+    const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
+    const char* gcol = frame_base + (size_t)chunk * 16;
     const int64_t rs = A.src_row_stride;
-    const int H = P.src_h;
+    const int Hm1 = P.src_h - 1;
+    const unsigned pair_bytes = (unsigned)(rs + W3);
+
     uint4 ra[PF], rb[PF];
-    auto load_pair = [&](int p, uint4& a, uint4& b) {
-      a = make_uint4(0, 0, 0, 0);
-      b = a;
-      if (vth && p < p1) {
-        a = __ldcs((const uint4*)(fbase + (int64_t)(2 * p) * rs));
-        if (2 * p + 1 < H) b = __ldcs((const uint4*)(fbase + (int64_t)(2 * p + 1) * rs));
-      }
-    };
 #pragma unroll
-    for (int u = 0; u < PF; ++u) load_pair(p0 + u, ra[u], rb[u]);
+    for (int u = 0; u < PF; ++u) {
+      const int pc = min(p0 + u, plast);
+      ra[u] = __ldcs((const uint4*)(gcol + (int64_t)(2 * pc) * rs));
+      rb[u] = __ldcs((const uint4*)(gcol + (int64_t)min(2 * pc + 1, Hm1) * rs));
+    }
+    if (tid == 0) {
+      for (int q = p0 + PF; q <= min(p0 + LA, plast); ++q)
+        l2_prefetch_bulk(frame_base + (int64_t)(2 * q) * rs, 2 * q + 1 <= Hm1 ? pair_bytes : (unsigned)W3);
+    }
 
-    auto accumulate = [&](unsigned (&acc)[16], unsigned w, const unsigned (&lo)[4], const unsigned (&hi)[4]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        acc[4 * q + 0] = __dp2a_lo(w, lo[q], acc[4 * q + 0]);
-        acc[4 * q + 1] = __dp2a_hi(w, lo[q], acc[4 * q + 1]);
-        acc[4 * q + 2] = __dp2a_lo(w, hi[q], acc[4 * q + 2]);
-        acc[4 * q + 3] = __dp2a_hi(w, hi[q], acc[4 * q + 3]);
-      }
-    };
-    auto stage = [&](unsigned (&acc)[16], unsigned short* dst) {
-      unsigned w[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        w[q] = (acc[2 * q] >> sh) | ((acc[2 * q + 1] >> sh) << 16);
-        acc[2 * q] = acc[2 * q + 1] = rnd;
-      }
-      uint4* d = (uint4*)(dst + tid * 16);
-      d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      d[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    };
-    auto reset = [&](unsigned (&acc)[16]) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = rnd;
-    };
+#define NEXAR_ACCUM(ACC, WV)                                \
+  {                                                         \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {         \
+      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], ACC[4 * q + 0]); \
+      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], ACC[4 * q + 1]); \
+      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], ACC[4 * q + 2]); \
+      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], ACC[4 * q + 3]); \
+    }                                                       \
+  }
+#define NEXAR_STAGE(ACC, DST)                                                   \
+  {                                                                             \
+    unsigned w_[8];                                                             \
+    _Pragma("unroll") for (int q = 0; q < 8; ++q) {                             \
+      w_[q] = (ACC[2 * q] >> sh) | ((ACC[2 * q + 1] >> sh) << 16);              \
+      ACC[2 * q] = rnd;                                                         \
+      ACC[2 * q + 1] = rnd;                                                     \
+    }                                                                           \
+    if (vstore) {                                                               \
+      uint4* d_ = (uint4*)((DST) + tid * 16);                                   \
+      d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                           \
+      d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                           \
+    }                                                                           \
+  }
+#define NEXAR_RESET(ACC)                                      \
+  {                                                           \
+    _Pragma("unroll") for (int q = 0; q < 16; ++q) ACC[q] = rnd; \
+  }
 
-    for (int pb = p0; pb < p1; pb += PF) {
+    for (int pb = p0; pb <= plast; pb += PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int p = pb + u;
-        if (p < p1) {
+        if (p <= plast) {
           const uint4 a = ra[u], b = rb[u];
-          load_pair(p + PF, ra[u], rb[u]);
-          const uint4 e = __ldg(P.pairs + p);
-          if (vth) {
-            orv |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | b.w);
-            unsigned lo[4], hi[4];
-            lo[0] = __byte_perm(a.x, b.x, 0x5140); hi[0] = __byte_perm(a.x, b.x, 0x7362);
-            lo[1] = __byte_perm(a.y, b.y, 0x5140); hi[1] = __byte_perm(a.y, b.y, 0x7362);
-            lo[2] = __byte_perm(a.z, b.z, 0x5140); hi[2] = __byte_perm(a.z, b.z, 0x7362);
-            lo[3] = __byte_perm(a.w, b.w, 0x5140); hi[3] = __byte_perm(a.w, b.w, 0x7362);
-            if (e.x) accumulate(acc0, e.x, lo, hi);
-            if (e.y) accumulate(acc1, e.y, lo, hi);
-            if (e.z) accumulate(acc2, e.z, lo, hi);
+          {  // refill this register slot with pair p + PF (clamped: the tail re-reads the last pair)
+            const int pc = min(p + PF, plast);
+            ra[u] = __ldcs((const uint4*)(gcol + (int64_t)(2 * pc) * rs));
+            rb[u] = __ldcs((const uint4*)(gcol + (int64_t)min(2 * pc + 1, Hm1) * rs));
           }
-          int row = (int)(e.w >> 2);
-          for (int n = (int)(e.w & 3u); n > 0; --n, ++row) {
-            const int s = row % 3;
-            if (row < i0 || row >= i1) {  // a neighbour band's row: drop it
-              if (vth) {
-                if (s == 0) reset(acc0); else if (s == 1) reset(acc1); else reset(acc2);
-              }
-              continue;
-            }
-            unsigned short* vcur = vb + buf * vstride;
-            if (vth) {
-              if (s == 0) stage(acc0, vcur); else if (s == 1) stage(acc1, vcur); else stage(acc2, vcur);
-            }
-            __syncthreads();
-            if (hth) {
-              const unsigned* src = (const unsigned*)vcur + hword;
-              float r = 0.0f, g = 0.0f, bl = 0.0f;
+          if (tid == 0 && p + LA <= plast)
+            l2_prefetch_bulk(frame_base + (int64_t)(2 * (p + LA)) * rs, 2 * (p + LA) + 1 <= Hm1 ? pair_bytes : (unsigned)W3);
+          const uint4 e = TB.e[p];
+          orv |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | b.w);
+          unsigned lo[4], hi[4];
+          lo[0] = __byte_perm(a.x, b.x, 0x5140); hi[0] = __byte_perm(a.x, b.x, 0x7362);
+          lo[1] = __byte_perm(a.y, b.y, 0x5140); hi[1] = __byte_perm(a.y, b.y, 0x7362);
+          lo[2] = __byte_perm(a.z, b.z, 0x5140); hi[2] = __byte_perm(a.z, b.z, 0x7362);
+          lo[3] = __byte_perm(a.w, b.w, 0x5140); hi[3] = __byte_perm(a.w, b.w, 0x7362);
+          if (e.x) NEXAR_ACCUM(acc0, e.x)
+          if (e.y) NEXAR_ACCUM(acc1, e.y)
+          if (e.w) {  // an output row finished with this pair
+            const int row = (int)(e.w >> 2);
+            const bool s1 = (e.w & 2u) != 0u;
+            if (row >= i0 && row < i1) {
+              unsigned short* vcur = vb + buf * vstride;
+              if (s1) NEXAR_STAGE(acc1, vcur) else NEXAR_STAGE(acc0, vcur)
+              __syncthreads();
+              if (hth) {
+                const unsigned* src = (const unsigned*)vcur + hword;
+                float r = 0.0f, g = 0.0f, bl = 0.0f;
 #pragma unroll
-              for (int k = 0; k < KX; k += 2) {
-                const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2];
-                r = fmaf(wx[k], magic_lo(w0), r);
-                g = fmaf(wx[k], magic_hi(w0), g);
-                bl = fmaf(wx[k], magic_lo(w1), bl);
-                r = fmaf(wx[k + 1], magic_hi(w1), r);
-                g = fmaf(wx[k + 1], magic_lo(w2), g);
-                bl = fmaf(wx[k + 1], magic_hi(w2), bl);
+                for (int k = 0; k < KX; k += 2) {
+                  const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2];
+                  r = fmaf(wx[k], magic_lo(w0), r);
+                  g = fmaf(wx[k], magic_hi(w0), g);
+                  bl = fmaf(wx[k], magic_lo(w1), bl);
+                  r = fmaf(wx[k + 1], magic_hi(w1), r);
+                  g = fmaf(wx[k + 1], magic_lo(w2), g);
+                  bl = fmaf(wx[k + 1], magic_hi(w2), bl);
+                }
+                r = (r - hbias) * post;
+                g = (g - hbias) * post;
+                bl = (bl - hbias) * post;
+                const int y = row + B.oy;
+                if (aug) {
+                  const float bright = cp->brightness;
+                  r = clamp01(__fmul_rn(bright, r));
+                  g = clamp01(__fmul_rn(bright, g));
+                  bl = clamp01(__fmul_rn(bright, bl));
+                  gsum += gray_of(r, g, bl);
+                  A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (xo - B.bx0)] = make_float4(r, g, bl, 0.0f);
+                } else {
+                  const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)xo * A.sx;
+                  if (A.normalize) {
+                    r = fmaf(r, A.nscale[0], A.nbias[0]);
+                    g = fmaf(g, A.nscale[1], A.nbias[1]);
+                    bl = fmaf(bl, A.nscale[2], A.nbias[2]);
+                  }
+                  store_out<DstT>(A.dst, o, r);
+                  store_out<DstT>(A.dst, o + A.sc, g);
+                  store_out<DstT>(A.dst, o + 2 * A.sc, bl);
+                }
               }
-              r = (r - hbias) * post;
-              g = (g - hbias) * post;
-              bl = (bl - hbias) * post;
-              const int y = row + B.oy;
-              if (aug) {
-                r = clamp01(__fmul_rn(bright, r));
-                g = clamp01(__fmul_rn(bright, g));
-                bl = clamp01(__fmul_rn(bright, bl));
-                gsum += gray_of(r, g, bl);
-                A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (xo - B.bx0)] = make_float4(r, g, bl, 0.0f);
-              } else {
-                const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)xo * A.sx;
-                store_out<DstT>(A.dst, o, fmaf(r, nsc[0], nbi[0]));
-                store_out<DstT>(A.dst, o + A.sc, fmaf(g, nsc[1], nbi[1]));
-                store_out<DstT>(A.dst, o + 2 * A.sc, fmaf(bl, nsc[2], nbi[2]));
-              }
+              buf ^= 1;
+            } else {  // a neighbour band's row: drop it
+              if (s1) NEXAR_RESET(acc1) else NEXAR_RESET(acc0)
             }
-            buf ^= 1;
+            if (e.z) {  // first tap of the slot's next row shares this pair
+              if (s1) NEXAR_ACCUM(acc1, e.z) else NEXAR_ACCUM(acc0, e.z)
+            }
           }
         }
       }
     }
+#undef NEXAR_ACCUM
+#undef NEXAR_STAGE
+#undef NEXAR_RESET
   }
 
   if (!aug) {
     const int Y0 = band == 0 ? 0 : i0 + B.oy;
     const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
     const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;
+    float nbi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
     for (int y = Y0; y < Y1; ++y) {
       const bool content_row = (y >= cy0 && y < cy1);
       for (int x = tid; x < P.cs; x += NT) {
@@ -1078,6 +1125,8 @@ __global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
   store_out<DstT>(A.dst, o + 2 * A.sc, b);
 }
 
+static thread_local PairTable g_pair_table;
+
 // ---------------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------------
@@ -1101,19 +1150,28 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const int kx = P.kx_al;
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
-    for (int pass = 0; pass < 2; ++pass) {
-      K.pass = pass;
-      if (pass == 0 && prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
-#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K)
-      if (need_threads <= 256) {
-        if (kx == 10) NEXAR_FAST(10, 256, 2); else if (kx == 14) NEXAR_FAST(14, 256, 2); else NEXAR_FAST(20, 256, 2);
-      } else {
-        if (kx == 10) NEXAR_FAST(10, 384, 1); else if (kx == 14) NEXAR_FAST(14, 384, 1); else NEXAR_FAST(20, 384, 1);
-      }
-#undef NEXAR_FAST
-      if (pass == 0 && prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
-      ++g_launches;
+    PairTable* tb = &g_pair_table;  // host staging of the kernel-parameter tap table
+    memset(tb, 0, sizeof(PairTable));
+    memcpy(tb->e, p->pairs.data(), p->pairs.size() * sizeof(uint4));
+    K.pass = 0;
+    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K, *tb)
+    if (need_threads <= 256) {
+      if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB); else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB); else NEXAR_FAST(20, 256, 2);
+    } else {
+      if (kx == 10) NEXAR_FAST(10, 384, 1); else if (kx == 14) NEXAR_FAST(14, 384, 1); else NEXAR_FAST(20, 384, 1);
     }
+#undef NEXAR_FAST
+    if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
+    // fix-up of clips whose maximum was <= 1 (not divided by 255): their values live in [0,1], below the
+    // resolution of the 15-bit staging, so the rare second pass uses the fp32 kernel.  Same band count:
+    // the gray partial sums are indexed by band.
+    K.pass = 1;
+    const size_t gsm = (size_t)P.src_w * 3 * sizeof(float);
+    if (gsm > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(resize_general_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    resize_general_kernel<SrcT, DstT><<<grid, 256, gsm, st>>>(P, K);
+    g_launches += 2;
   } else {
     nbands = imax(1, imin(kMaxBands, vis_rows / 24));
     const size_t smem = (size_t)P.src_w * 3 * sizeof(float);
