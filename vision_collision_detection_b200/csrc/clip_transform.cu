@@ -82,8 +82,8 @@ struct NexarPlan {
 // down-scale keeps at most two output rows alive at any source row (ymin[i+2] >= ymax[i]), so two
 // rotating accumulator slots suffice (out row i lives in slot i % 2).  The kernel consumes source rows
 // in PAIRS through dp2a; table entry p = {w slot0, w slot1, w post, emit} with w = u16x2 (row 2p | row
-// 2p+1 << 16), emit = 0 or (1 | slot << 1 | out_row << 2) when an output row's last tap lies in this
-// pair, and "w post" the first tap of the NEXT row of that slot when it falls in the same pair (it is
+// 2p+1 << 16), emit = bit0 (an output row's last tap lies in this pair) | slot << 1 | begin0 << 2 |
+// begin1 << 3 (the slot's accumulators restart at this pair) | out_row << 4, and "w post" the first tap of the NEXT row of that slot when it falls in the same pair (it is
 // accumulated after the finished row has been flushed).  Returns false when the geometry does not fit.
 static const int kMaxPairs = 1024;
 static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
@@ -122,20 +122,27 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
     if (q[arg] < 0 || q[arg] > 65535) return false;
     const int slot = i % 2;
     const int prev_last = i >= 2 ? p->ystart[i - 2] + p->ycount[i - 2] - 1 : -1;  // last tap of the slot's previous row
+    bool begun = false;
     for (int k = 0; k < yc; ++k) {
       const int y = ys + k;
       uint4& e = p->pairs[y / 2];
       if (prev_last >= 0 && prev_last / 2 == y / 2) {
         if (!(y & 1) || e.z) return false;
-        e.z = (unsigned)q[k] << 16;
+        e.z = (unsigned)q[k] << 16;  // accumulated with "begin" semantics after the flush
+        if (q[k]) begun = true;
       } else {
         unsigned& ws = slot ? e.y : e.x;
+        if (!begun && q[k]) {  // first non-zero tap of the row: the accumulators restart from the rounding constant
+          if (ws) return false;
+          e.w |= slot ? 8u : 4u;
+          begun = true;
+        }
         ws |= (unsigned)q[k] << (16 * (y & 1));
       }
     }
     unsigned& em = p->pairs[(ys + yc - 1) / 2].w;
-    if (em) return false;  // one flush per pair
-    em = 1u | ((unsigned)slot << 1) | ((unsigned)i << 2);
+    if (em & 1u) return false;  // one flush per pair
+    em |= 1u | ((unsigned)slot << 1) | ((unsigned)i << 4);
   }
   p->xstart_al.assign(g.resize_w, 0);
   p->xwt_al.assign((size_t)g.resize_w * kx_al, 0.f);
@@ -619,8 +626,8 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 //
 // Down-scaling (>= 2x vertically) uint8 frames whose rows are a multiple of 16 bytes.  A CTA owns
 // one band of resized rows of one frame and streams the source rows it needs exactly once, two rows
-// per step.  Every thread keeps one 16-byte column chunk: 128-bit coalesced streaming loads, PF
-// pairs ahead in registers, with one elected thread pushing the rows LOOKAHEAD pairs ahead into L2
+// per step.  Every thread keeps one 16-byte column chunk: 128-bit coalesced streaming loads, one
+// pair ahead in registers (ping-pong), while warp 0 pushes the rows LOOKAHEAD pairs ahead into L2
 // through the bulk-copy engine (cp.async.bulk.prefetch.L2).  The two rows' bytes are interleaved
 // with PRMT and fed to dp2a against the 16-bit fixed-point taps of the (at most two) output rows
 // alive at that height.  The tap table lives in the kernel parameters (constant bank), so the
@@ -642,10 +649,10 @@ struct PairTable {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) {
+  return __ldcs((const uint4*)(base + off));
+}
 
-#ifndef NEXAR_PF
-#define NEXAR_PF 2
-#endif
 #ifndef NEXAR_MINB
 #define NEXAR_MINB 3
 #endif
@@ -653,13 +660,19 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) 
 #define NEXAR_LOOKAHEAD 12
 #endif
 
+// table entry .w bits
+#define NEXAR_E_EMIT 1u
+#define NEXAR_E_SLOT 2u
+#define NEXAR_E_BEGIN0 4u
+#define NEXAR_E_BEGIN1 8u
+#define NEXAR_E_ROWSHIFT 4
+
 template <int KX, int NT, int MINB, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, const __grid_constant__ PairTable TB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
-  constexpr int PF = NEXAR_PF;         // row pairs in flight per thread (registers)
-  constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine
+  constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine (multiple of 4)
   const int tid = threadIdx.x;
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
@@ -700,147 +713,155 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     float hbias = 0.0f;
 #pragma unroll
     for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
-    const int hword = (P.xstart_al[j] * 3) >> 1;  // 32-bit word offset of the first tap in the staging row
+    const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
     const float post = scale * (1.0f / 128.0f);
+    // where this thread's pixel goes (row term added per output row)
+    const int64_t opix = dbase + (int64_t)xo * A.sx;
+    float4* ipix = A.inter + ((size_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0);
 
     // ---- vertical pass state ----
     const int sh = P.shift - 7;
     const unsigned rnd = 1u << (sh - 1);
     unsigned acc0[16], acc1[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = rnd;
-    int buf = 0;
+    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = 0u;
     const int p0 = P.ystart[i0] >> 1;
     const int plast = (P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1;  // inclusive
     const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
     const bool vstore = tid < nchunks;
     const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
-    const char* gcol = frame_base + (size_t)chunk * 16;
-    const int64_t rs = A.src_row_stride;
-    const int Hm1 = P.src_h - 1;
-    const unsigned pair_bytes = (unsigned)(rs + W3);
+    const unsigned rs = (unsigned)A.src_row_stride;  // a frame is < 4 GB: 32-bit offsets from the frame base
+    const unsigned step = 2u * rs;
+    const unsigned off_odd_max = (unsigned)(P.src_h - 1) * rs + (unsigned)chunk * 16u;  // last row (odd heights)
+    const unsigned off_last = (unsigned)(2 * plast) * rs + (unsigned)chunk * 16u;
+    unsigned off = (unsigned)(2 * p0) * rs + (unsigned)chunk * 16u;
+    unsigned sbuf = (unsigned)tid * 32u;  // byte offset of this thread's staging slot in the current buffer
+    unsigned hbuf = hbyte;
+    unsigned dlt = (unsigned)vstride * 2u;  // +-bytes to the other staging buffer
 
-    uint4 ra[PF], rb[PF];
-#pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int pc = min(p0 + u, plast);
-      ra[u] = __ldcs((const uint4*)(gcol + (int64_t)(2 * pc) * rs));
-      rb[u] = __ldcs((const uint4*)(gcol + (int64_t)min(2 * pc + 1, Hm1) * rs));
-    }
-    if (tid == 0) {
-      for (int q = p0 + PF; q <= min(p0 + LA, plast); ++q)
-        l2_prefetch_bulk(frame_base + (int64_t)(2 * q) * rs, 2 * q + 1 <= Hm1 ? pair_bytes : (unsigned)W3);
+    uint4 a0 = ld_stream(frame_base, off), b0 = ld_stream(frame_base, min(off + rs, off_odd_max));
+    uint4 a1, b1;
+    if (tid < 32) {
+      const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
+      if (tid == 0 && q1 >= q0)
+        l2_prefetch_bulk(frame_base + (size_t)(2 * q0) * rs, (unsigned)min((int64_t)(2 * (q1 - q0 + 1)) * rs, (int64_t)P.src_h * rs - (int64_t)(2 * q0) * rs));
     }
 
-#define NEXAR_ACCUM(ACC, WV)                                \
-  {                                                         \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) {         \
+#define NEXAR_ACCUM(ACC, WV)                                 \
+  {                                                          \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {          \
       ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], ACC[4 * q + 0]); \
       ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], ACC[4 * q + 1]); \
       ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], ACC[4 * q + 2]); \
       ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], ACC[4 * q + 3]); \
-    }                                                       \
+    }                                                        \
   }
-#define NEXAR_STAGE(ACC, DST)                                                   \
-  {                                                                             \
-    unsigned w_[8];                                                             \
-    _Pragma("unroll") for (int q = 0; q < 8; ++q) {                             \
-      w_[q] = (ACC[2 * q] >> sh) | ((ACC[2 * q + 1] >> sh) << 16);              \
-      ACC[2 * q] = rnd;                                                         \
-      ACC[2 * q + 1] = rnd;                                                     \
-    }                                                                           \
-    if (vstore) {                                                               \
-      uint4* d_ = (uint4*)((DST) + tid * 16);                                   \
-      d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                           \
-      d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                           \
-    }                                                                           \
+#define NEXAR_ACCUM_BEGIN(ACC, WV)                  \
+  {                                                 \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
+      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], rnd);   \
+      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], rnd);   \
+      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], rnd);   \
+      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], rnd);   \
+    }                                               \
   }
-#define NEXAR_RESET(ACC)                                      \
-  {                                                           \
-    _Pragma("unroll") for (int q = 0; q < 16; ++q) ACC[q] = rnd; \
+#define NEXAR_STAGE(ACC)                                                                      \
+  {                                                                                           \
+    unsigned w_[8];                                                                           \
+    _Pragma("unroll") for (int q = 0; q < 8; ++q)                                             \
+        w_[q] = __byte_perm(ACC[2 * q] >> sh, ACC[2 * q + 1] << (16 - sh), 0x7610);           \
+    if (vstore) {                                                                             \
+      uint4* d_ = (uint4*)(smem_raw + sbuf);                                                  \
+      d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                                         \
+      d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
+    }                                                                                         \
+  }
+// One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk, NA/NB receive the next pair.
+#define NEXAR_PAIR(CA, CB, NA, NB)                                                                         \
+  {                                                                                                        \
+    off = min(off + step, off_last); /* the tail re-reads the last pair */                                 \
+    NA = ld_stream(frame_base, off);                                                                       \
+    NB = ld_stream(frame_base, min(off + rs, off_odd_max));                                                \
+    const uint4 e = TB.e[p];                                                                               \
+    orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
+    unsigned lo[4], hi[4];                                                                                 \
+    lo[0] = __byte_perm(CA.x, CB.x, 0x5140); hi[0] = __byte_perm(CA.x, CB.x, 0x7362);                      \
+    lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
+    lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
+    lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
+    if (e.x) {                                                                                             \
+      if (e.w & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, e.x) else NEXAR_ACCUM(acc0, e.x)                   \
+    }                                                                                                      \
+    if (e.y) {                                                                                             \
+      if (e.w & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, e.y) else NEXAR_ACCUM(acc1, e.y)                   \
+    }                                                                                                      \
+    if (e.w & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
+      const int row = (int)(e.w >> NEXAR_E_ROWSHIFT);                                                      \
+      const bool s1 = (e.w & NEXAR_E_SLOT) != 0u;                                                          \
+      if (row >= i0 && row < i1) {                                                                         \
+        if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
+        __syncthreads();                                                                                   \
+        if (hth) {                                                                                         \
+          const unsigned* src = (const unsigned*)(smem_raw + hbuf);                                        \
+          float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
+          _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
+            const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2]; \
+            r = fmaf(wx[k], magic_lo(w0), r);                                                              \
+            g = fmaf(wx[k], magic_hi(w0), g);                                                              \
+            bl = fmaf(wx[k], magic_lo(w1), bl);                                                            \
+            r = fmaf(wx[k + 1], magic_hi(w1), r);                                                          \
+            g = fmaf(wx[k + 1], magic_lo(w2), g);                                                          \
+            bl = fmaf(wx[k + 1], magic_hi(w2), bl);                                                        \
+          }                                                                                                \
+          r = (r - hbias) * post;                                                                          \
+          g = (g - hbias) * post;                                                                          \
+          bl = (bl - hbias) * post;                                                                        \
+          const int y = row + B.oy;                                                                        \
+          if (aug) {                                                                                       \
+            const float bright = cp->brightness;                                                           \
+            r = clamp01(__fmul_rn(bright, r));                                                             \
+            g = clamp01(__fmul_rn(bright, g));                                                             \
+            bl = clamp01(__fmul_rn(bright, bl));                                                           \
+            gsum += gray_of(r, g, bl);                                                                     \
+            ipix[(size_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                                          \
+          } else {                                                                                         \
+            const int64_t o = opix + (int64_t)y * A.sy;                                                    \
+            if (A.normalize) {                                                                             \
+              r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
+              g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
+              bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
+            }                                                                                              \
+            store_out<DstT>(A.dst, o, r);                                                                  \
+            store_out<DstT>(A.dst, o + A.sc, g);                                                           \
+            store_out<DstT>(A.dst, o + 2 * A.sc, bl);                                                      \
+          }                                                                                                \
+        }                                                                                                  \
+        sbuf += dlt; hbuf += dlt; dlt = 0u - dlt; /* other staging buffer */                                \
+      }                                                                                                    \
+      if (e.z) { /* first tap of the slot's next row shares this pair */                                   \
+        if (s1) NEXAR_ACCUM_BEGIN(acc1, e.z) else NEXAR_ACCUM_BEGIN(acc0, e.z)                             \
+      }                                                                                                    \
+    }                                                                                                      \
+    if ((p & 3) == 3 && tid < 32) { /* warp 0: next 4 pairs, LA ahead, into L2 */                          \
+      const int q0 = p + 1 + LA;                                                                           \
+      if (tid == 0 && q0 <= plast) {                                                                       \
+        const int64_t o0 = (int64_t)(2 * q0) * rs;                                                         \
+        l2_prefetch_bulk(frame_base + o0, (unsigned)min((int64_t)8 * rs, (int64_t)P.src_h * rs - o0));     \
+      }                                                                                                    \
+    }                                                                                                      \
   }
 
-    for (int pb = p0; pb <= plast; pb += PF) {
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int p = pb + u;
-        if (p <= plast) {
-          const uint4 a = ra[u], b = rb[u];
-          {  // refill this register slot with pair p + PF (clamped: the tail re-reads the last pair)
-            const int pc = min(p + PF, plast);
-            ra[u] = __ldcs((const uint4*)(gcol + (int64_t)(2 * pc) * rs));
-            rb[u] = __ldcs((const uint4*)(gcol + (int64_t)min(2 * pc + 1, Hm1) * rs));
-          }
-          if (tid == 0 && p + LA <= plast)
-            l2_prefetch_bulk(frame_base + (int64_t)(2 * (p + LA)) * rs, 2 * (p + LA) + 1 <= Hm1 ? pair_bytes : (unsigned)W3);
-          const uint4 e = TB.e[p];
-          orv |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | b.w);
-          unsigned lo[4], hi[4];
-          lo[0] = __byte_perm(a.x, b.x, 0x5140); hi[0] = __byte_perm(a.x, b.x, 0x7362);
-          lo[1] = __byte_perm(a.y, b.y, 0x5140); hi[1] = __byte_perm(a.y, b.y, 0x7362);
-          lo[2] = __byte_perm(a.z, b.z, 0x5140); hi[2] = __byte_perm(a.z, b.z, 0x7362);
-          lo[3] = __byte_perm(a.w, b.w, 0x5140); hi[3] = __byte_perm(a.w, b.w, 0x7362);
-          if (e.x) NEXAR_ACCUM(acc0, e.x)
-          if (e.y) NEXAR_ACCUM(acc1, e.y)
-          if (e.w) {  // an output row finished with this pair
-            const int row = (int)(e.w >> 2);
-            const bool s1 = (e.w & 2u) != 0u;
-            if (row >= i0 && row < i1) {
-              unsigned short* vcur = vb + buf * vstride;
-              if (s1) NEXAR_STAGE(acc1, vcur) else NEXAR_STAGE(acc0, vcur)
-              __syncthreads();
-              if (hth) {
-                const unsigned* src = (const unsigned*)vcur + hword;
-                float r = 0.0f, g = 0.0f, bl = 0.0f;
-#pragma unroll
-                for (int k = 0; k < KX; k += 2) {
-                  const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2];
-                  r = fmaf(wx[k], magic_lo(w0), r);
-                  g = fmaf(wx[k], magic_hi(w0), g);
-                  bl = fmaf(wx[k], magic_lo(w1), bl);
-                  r = fmaf(wx[k + 1], magic_hi(w1), r);
-                  g = fmaf(wx[k + 1], magic_lo(w2), g);
-                  bl = fmaf(wx[k + 1], magic_hi(w2), bl);
-                }
-                r = (r - hbias) * post;
-                g = (g - hbias) * post;
-                bl = (bl - hbias) * post;
-                const int y = row + B.oy;
-                if (aug) {
-                  const float bright = cp->brightness;
-                  r = clamp01(__fmul_rn(bright, r));
-                  g = clamp01(__fmul_rn(bright, g));
-                  bl = clamp01(__fmul_rn(bright, bl));
-                  gsum += gray_of(r, g, bl);
-                  A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (xo - B.bx0)] = make_float4(r, g, bl, 0.0f);
-                } else {
-                  const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)xo * A.sx;
-                  if (A.normalize) {
-                    r = fmaf(r, A.nscale[0], A.nbias[0]);
-                    g = fmaf(g, A.nscale[1], A.nbias[1]);
-                    bl = fmaf(bl, A.nscale[2], A.nbias[2]);
-                  }
-                  store_out<DstT>(A.dst, o, r);
-                  store_out<DstT>(A.dst, o + A.sc, g);
-                  store_out<DstT>(A.dst, o + 2 * A.sc, bl);
-                }
-              }
-              buf ^= 1;
-            } else {  // a neighbour band's row: drop it
-              if (s1) NEXAR_RESET(acc1) else NEXAR_RESET(acc0)
-            }
-            if (e.z) {  // first tap of the slot's next row shares this pair
-              if (s1) NEXAR_ACCUM(acc1, e.z) else NEXAR_ACCUM(acc0, e.z)
-            }
-          }
-        }
-      }
+    for (int p = p0; p <= plast; ++p) {
+      NEXAR_PAIR(a0, b0, a1, b1)
+      if (++p > plast) break;
+      NEXAR_PAIR(a1, b1, a0, b0)
     }
+#undef NEXAR_PAIR
 #undef NEXAR_ACCUM
+#undef NEXAR_ACCUM_BEGIN
 #undef NEXAR_STAGE
-#undef NEXAR_RESET
   }
 
   if (!aug) {
