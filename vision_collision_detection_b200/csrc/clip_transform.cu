@@ -89,7 +89,7 @@ static const int kMaxPairs = 1024;
 static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
   const NexarGeometry& g = p->g;
   if (p->src_dtype != NEXAR_SRC_U8) return false;
-  if ((g.src_w * 3) % 16 != 0 || g.src_w * 3 / 16 > 384) return false;
+  if ((g.src_w * 3) % 16 != 0 || g.src_w * 3 / 16 > 384 || (g.src_h & 1)) return false;  // rows are consumed in pairs
   if (g.src_h < 2 * g.resize_h || g.src_w < g.resize_w) return false;  // vertical down-scale by >= 2
   if (imin_host(g.resize_w, g.canvas) > 384) return false;
   kx_al = kx + 1;
@@ -381,6 +381,7 @@ struct PairTable;
 struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
   float* gray_partial;  // [2][n_frames][kMaxBands]
+  float4* pad_colour;   // [n_frames] colour of a zero (pad) pixel after the colour chain (written by K2)
   float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
   size_t total;
@@ -396,6 +397,8 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base) {
   off = align_up(off + (size_t)n_clips * sizeof(unsigned), 256);
   w.gray_partial = (float*)(b + off);
   off = align_up(off + 2 * nf * kMaxBands * sizeof(float), 256);
+  w.pad_colour = (float4*)(b + off);
+  off = align_up(off + nf * sizeof(float4), 256);
   w.inter = (float4*)(b + off);
   off = align_up(off + nf * bh * bw * sizeof(float4), 256);
   w.canvas = (float*)(b + off);
@@ -424,6 +427,7 @@ struct KArgs {
   float nscale[3], nbias[3];  // out = v * nscale + nbias  ((v - mean) / std)
   unsigned* clip_max;
   float* gray_partial;
+  float4* pad_colour;
   float4* inter;
   float* canvas;
   int n_frames;
@@ -719,7 +723,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const float post = scale * (1.0f / 128.0f);
     // where this thread's pixel goes (row term added per output row)
     const int64_t opix = dbase + (int64_t)xo * A.sx;
-    float4* ipix = A.inter + ((size_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0);
+    float4* ipix = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0);
 
     // ---- vertical pass state ----
     const int sh = P.shift - 7;
@@ -734,14 +738,13 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
     const unsigned rs = (unsigned)A.src_row_stride;  // a frame is < 4 GB: 32-bit offsets from the frame base
     const unsigned step = 2u * rs;
-    const unsigned off_odd_max = (unsigned)(P.src_h - 1) * rs + (unsigned)chunk * 16u;  // last row (odd heights)
     const unsigned off_last = (unsigned)(2 * plast) * rs + (unsigned)chunk * 16u;
     unsigned off = (unsigned)(2 * p0) * rs + (unsigned)chunk * 16u;
     unsigned sbuf = (unsigned)tid * 32u;  // byte offset of this thread's staging slot in the current buffer
     unsigned hbuf = hbyte;
     unsigned dlt = (unsigned)vstride * 2u;  // +-bytes to the other staging buffer
 
-    uint4 a0 = ld_stream(frame_base, off), b0 = ld_stream(frame_base, min(off + rs, off_odd_max));
+    uint4 a0 = ld_stream(frame_base, off), b0 = ld_stream(frame_base, off + rs);
     uint4 a1, b1;
     if (tid < 32) {
       const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
@@ -783,7 +786,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   {                                                                                                        \
     off = min(off + step, off_last); /* the tail re-reads the last pair */                                 \
     NA = ld_stream(frame_base, off);                                                                       \
-    NB = ld_stream(frame_base, min(off + rs, off_odd_max));                                                \
+    NB = ld_stream(frame_base, off + rs);                                                                  \
     const uint4 e = TB.e[p];                                                                               \
     orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
     unsigned lo[4], hi[4];                                                                                 \
@@ -791,11 +794,16 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
-    if (e.x) {                                                                                             \
-      if (e.w & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, e.x) else NEXAR_ACCUM(acc0, e.x)                   \
-    }                                                                                                      \
-    if (e.y) {                                                                                             \
-      if (e.w & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, e.y) else NEXAR_ACCUM(acc1, e.y)                   \
+    if (e.w == 0u) { /* common case: no row starts or ends in this pair */                                \
+      if (e.x) NEXAR_ACCUM(acc0, e.x)                                                                      \
+      if (e.y) NEXAR_ACCUM(acc1, e.y)                                                                      \
+    } else {                                                                                               \
+      if (e.x) {                                                                                           \
+        if (e.w & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, e.x) else NEXAR_ACCUM(acc0, e.x)                 \
+      }                                                                                                    \
+      if (e.y) {                                                                                           \
+        if (e.w & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, e.y) else NEXAR_ACCUM(acc1, e.y)                 \
+      }                                                                                                    \
     }                                                                                                      \
     if (e.w & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
       const int row = (int)(e.w >> NEXAR_E_ROWSHIFT);                                                      \
@@ -825,7 +833,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
             g = clamp01(__fmul_rn(bright, g));                                                             \
             bl = clamp01(__fmul_rn(bright, bl));                                                           \
             gsum += gray_of(r, g, bl);                                                                     \
-            ipix[(size_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                                          \
+            ipix[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                                          \
           } else {                                                                                         \
             const int64_t o = opix + (int64_t)y * A.sy;                                                    \
             if (A.normalize) {                                                                             \
@@ -895,53 +903,46 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
 // colour chain on one pixel: contrast -> saturation -> hue  (tv:_functional_tensor.py:181-321)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void hue_shift(float& r, float& g, float& b, float hue) {
+  // tv _rgb2hsv -> (h + hue) % 1 -> _hsv2rgb.  Divisions go through the fast reciprocal: the result
+  // feeds a 1e-3 gate, and every branch of the hexcone is continuous at its boundaries.
   const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
   const bool eqc = maxc == minc;
-  const float cr = __fsub_rn(maxc, minc);
-  const float s = __fdiv_rn(cr, eqc ? 1.0f : maxc);
-  const float div = eqc ? 1.0f : cr;
-  const float rc = __fdiv_rn(__fsub_rn(maxc, r), div);
-  const float gc = __fdiv_rn(__fsub_rn(maxc, g), div);
-  const float bc = __fdiv_rn(__fsub_rn(maxc, b), div);
-  float h;
-  if (maxc == r)
-    h = __fsub_rn(bc, gc);
-  else if (maxc == g)
-    h = __fsub_rn(__fadd_rn(2.0f, rc), bc);
-  else
-    h = __fsub_rn(__fadd_rn(4.0f, gc), rc);
-  h = fmodf(__fadd_rn(__fdiv_rn(h, 6.0f), 1.0f), 1.0f);
-  // (h + hue) % 1.0 — python-style remainder (ATen remainder: fmod, then fix the sign)
-  float hh = fmodf(__fadd_rn(h, hue), 1.0f);
-  if (hh != 0.0f && hh < 0.0f) hh = __fadd_rn(hh, 1.0f);
+  const float cr = maxc - minc;
+  const float s = __fdividef(cr, eqc ? 1.0f : maxc);
+  const float inv = __fdividef(1.0f, eqc ? 1.0f : cr);
+  const float rc = (maxc - r) * inv, gc = (maxc - g) * inv, bc = (maxc - b) * inv;
+  float h = (maxc == r) ? (bc - gc) : (maxc == g) ? (2.0f + rc - bc) : (4.0f + gc - rc);
+  h = h * (1.0f / 6.0f) + 1.0f;
+  h -= floorf(h);                       // fmod(h/6 + 1, 1)
+  float hh = h + hue;
+  hh -= floorf(hh);                     // python-style (h + hue) % 1.0
   const float v = maxc;
-  const float h6 = __fmul_rn(hh, 6.0f);
+  const float h6 = hh * 6.0f;
   const float fi = floorf(h6);
-  const float f = __fsub_rn(h6, fi);
-  int i = (int)fi % 6;
-  if (i < 0) i += 6;
-  const float p = clamp01(__fmul_rn(v, __fsub_rn(1.0f, s)));
-  const float q = clamp01(__fmul_rn(v, __fsub_rn(1.0f, __fmul_rn(s, f))));
-  const float tt = clamp01(__fmul_rn(v, __fsub_rn(1.0f, __fmul_rn(s, __fsub_rn(1.0f, f)))));
-  switch (i) {
-    case 0: r = v; g = tt; b = p; break;
-    case 1: r = q; g = v; b = p; break;
-    case 2: r = p; g = v; b = tt; break;
-    case 3: r = p; g = q; b = v; break;
-    case 4: r = tt; g = p; b = v; break;
-    default: r = v; g = p; b = q; break;
-  }
+  const float f = h6 - fi;
+  int i = (int)fi;
+  i = i >= 6 ? i - 6 : i;
+  const float p = clamp01(v * (1.0f - s));
+  const float q = clamp01(v * (1.0f - s * f));
+  const float tt = clamp01(v * (1.0f - s * (1.0f - f)));
+  r = (i == 0 || i == 5) ? v : (i == 1) ? q : (i == 4) ? tt : p;
+  g = (i == 1 || i == 2) ? v : (i == 0) ? tt : (i == 3) ? q : p;
+  b = (i == 3 || i == 4) ? v : (i == 2) ? tt : (i == 5) ? q : p;
 }
 
-__device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const NexarClipParams* cp, float mean) {
-  r = blend(r, mean, cp->contrast, cp->contrast_q);
-  g = blend(g, mean, cp->contrast, cp->contrast_q);
-  b = blend(b, mean, cp->contrast, cp->contrast_q);
-  const float gy = gray_of(r, g, b);
-  r = blend(r, gy, cp->saturation, cp->saturation_q);
-  g = blend(g, gy, cp->saturation, cp->saturation_q);
-  b = blend(b, gy, cp->saturation, cp->saturation_q);
-  hue_shift(r, g, b, cp->hue);
+struct ColourParams {
+  float cmean, contrast, saturation, saturation_q, hue;  // cmean = contrast_q * frame mean
+};
+__device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const ColourParams& c) {
+  // tv _blend: (ratio * img + (1 - ratio) * other).clamp(0, 1)
+  r = clamp01(__fadd_rn(__fmul_rn(c.contrast, r), c.cmean));
+  g = clamp01(__fadd_rn(__fmul_rn(c.contrast, g), c.cmean));
+  b = clamp01(__fadd_rn(__fmul_rn(c.contrast, b), c.cmean));
+  const float gq = __fmul_rn(c.saturation_q, gray_of(r, g, b));
+  r = clamp01(__fadd_rn(__fmul_rn(c.saturation, r), gq));
+  g = clamp01(__fadd_rn(__fmul_rn(c.saturation, g), gq));
+  b = clamp01(__fadd_rn(__fmul_rn(c.saturation, b), gq));
+  hue_shift(r, g, b, c.hue);
 }
 
 __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, int frame, int slot, int nbands) {
@@ -951,23 +952,44 @@ __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, in
   return s / (float)(P.cs * P.cs);
 }
 
-// K2: contrast/saturation/hue in place on the content box.
-__global__ void __launch_bounds__(256) colour_kernel(DevPlan P, KArgs A, int nbands) {
+// K2: contrast/saturation/hue in place on the frame's content box (which always fills the
+// [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them).
+// Block (0, frame) also publishes the colour a zero pad pixel takes, for K3.
+constexpr int kColourPerThread = 4;
+__global__ void __launch_bounds__(256) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, int nbands) {
+  __shared__ ColourParams S;
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
   const NexarClipParams* cp = A.params + clip;
   if (!(cp->flags & NEXAR_AUG)) return;
-  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
-  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, cp->flags & NEXAR_FLIP);
-  const int h = B.by1 - B.by0, w = B.bx1 - B.bx0;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= h * w) return;
-  const float mean = frame_mean(A, P, frame, slot, nbands);
-  const int y = idx / w, x = idx - y * w;
-  float4* p = A.inter + ((size_t)frame * A.bh + y) * A.bw + x;
-  float4 v = *p;
-  colour_chain(v.x, v.y, v.z, cp, mean);
-  *p = v;
+  if (threadIdx.x == 0) {
+    const int slot = A.clip_max[clip] != 0u ? 0 : 1;
+    S.cmean = __fmul_rn(cp->contrast_q, frame_mean(A, P, frame, slot, nbands));
+    S.contrast = cp->contrast;
+    S.saturation = cp->saturation;
+    S.saturation_q = cp->saturation_q;
+    S.hue = cp->hue;
+    if (blockIdx.x == 0) {
+      float r = 0.0f, g = 0.0f, b = 0.0f;
+      colour_chain(r, g, b, S);
+      A.pad_colour[frame] = make_float4(r, g, b, 0.0f);
+    }
+  }
+  __syncthreads();
+  const ColourParams c = S;
+  const int n = A.bh * A.bw;
+  float4* base = A.inter + (size_t)frame * n;
+  const int i0 = blockIdx.x * (256 * kColourPerThread) + threadIdx.x;
+  float4 v[kColourPerThread];
+#pragma unroll
+  for (int k = 0; k < kColourPerThread; ++k)
+    if (i0 + k * 256 < n) v[k] = base[i0 + k * 256];
+#pragma unroll
+  for (int k = 0; k < kColourPerThread; ++k)
+    if (i0 + k * 256 < n) {
+      colour_chain(v[k].x, v[k].y, v[k].z, c);
+      base[i0 + k * 256] = v[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1012,97 +1034,124 @@ __device__ __forceinline__ void point_effects(float& r, float& g, float& b, cons
   }
 }
 
+// Thread block = 32 x 32 output pixels of one frame, four rows per thread.  A tile whose four
+// corners map (affine maps are linear, so the corners bound the tile) strictly inside the canvas and
+// entirely into the pad band beside the content is filled with the constant pad colour without
+// touching the intermediate.
+constexpr int kGeoRows = 4;
 template <typename DstT>
-__global__ void __launch_bounds__(256) geometry_kernel(DevPlan P, KArgs A, int nbands) {
-  __shared__ float padc[3];
-  const int frame = blockIdx.y;
+__global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  const int frame = blockIdx.z;
   const int clip = frame / A.T;
   const int t = frame - clip * A.T;
   const NexarClipParams* cp = A.params + clip;
   const unsigned flags = cp->flags;
   if (!(flags & NEXAR_AUG)) return;
-  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
   const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flags & NEXAR_FLIP);
   const int cs = P.cs;
-  if (threadIdx.x == 0) {
-    // colour of a zero (pad) pixel after brightness/contrast/saturation/hue
-    float r = 0.0f, g = 0.0f, b = 0.0f;
-    colour_chain(r, g, b, cp, frame_mean(A, P, frame, slot, nbands));
-    padc[0] = r; padc[1] = g; padc[2] = b;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + tx, ybase = blockIdx.y * 32 + ty;
+  const float half = (float)cs * 0.5f;
+  const float4 padv = A.pad_colour[frame];
+  const float g0 = cp->grid[0], g1 = cp->grid[1], g2 = cp->grid[2], g3 = cp->grid[3], g4 = cp->grid[4], g5 = cp->grid[5];
+  bool fill = false;
+  if (flags & NEXAR_AFFINE) {
+    float ymin = 1e30f, ymax = -1e30f, xmin = 1e30f, xmax = -1e30f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float xb = (float)min((int)blockIdx.x * 32 + (c & 1) * 31, cs - 1) - half + 0.5f;
+      const float yb = (float)min((int)blockIdx.y * 32 + (c >> 1) * 31, cs - 1) - half + 0.5f;
+      const float sx = fmaf(fmaf(yb, g1, xb * g0) + g2 + 1.0f, (float)cs, -1.0f) * 0.5f;
+      const float sy = fmaf(fmaf(yb, g4, xb * g3) + g5 + 1.0f, (float)cs, -1.0f) * 0.5f;
+      xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
+      ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+    }
+    // 0.01 px of slack for fp rounding differences between the corner and per-pixel evaluation
+    const bool inside = xmin >= 0.01f && xmax <= (float)(cs - 1) - 0.01f && ymin >= 0.01f && ymax <= (float)(cs - 1) - 0.01f;
+    const bool above = ymax + 1.01f < (float)B.by0, below = ymin - 0.01f >= (float)B.by1;
+    const bool left = xmax + 1.01f < (float)B.bx0, right = xmin - 0.01f >= (float)B.bx1;
+    fill = inside && (above || below || left || right);
   }
-  __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cs * cs) return;
-  const int y = idx / cs, x = idx - y * cs;
-  const float4* fr = A.inter + (size_t)frame * A.bh * A.bw;
-  auto fetch = [&](int yy, int xx, float& r, float& g, float& b) {
-    if (yy >= B.by0 && yy < B.by1 && xx >= B.bx0 && xx < B.bx1) {
-      const float4 v = fr[(size_t)(yy - B.by0) * A.bw + (xx - B.bx0)];
+  if (x >= cs) return;
+  const float4* fr = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;  // indexed by canvas (y, x)
+  const float xb = (float)x - half + 0.5f;
+  const int64_t obase = (int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)x * A.sx;
+  const bool tail_fx = (flags & (NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT)) != 0u;
+#pragma unroll
+  for (int k = 0; k < kGeoRows; ++k) {
+    const int y = ybase + 8 * k;
+    if (y >= cs) break;
+    float r, g, b;
+    if (fill) {
+      r = padv.x; g = padv.y; b = padv.z;
+    } else if (flags & NEXAR_AFFINE) {
+      // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
+      const float yb = (float)y - half + 0.5f;
+      const float gx = fmaf(yb, g1, xb * g0) + g2;
+      const float gy = fmaf(yb, g4, xb * g3) + g5;
+      const float ix = fmaf(gx + 1.0f, (float)cs, -1.0f) * 0.5f;
+      const float iy = fmaf(gy + 1.0f, (float)cs, -1.0f) * 0.5f;
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const float wx1 = ix - x0f, wy1 = iy - y0f;
+      const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+      // clamp before the int cast so wild matrices cannot overflow
+      const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)cs + 1.0f);
+      const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)cs + 1.0f);
+      const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
+      const bool iny0 = (unsigned)y0 < (unsigned)cs, iny1 = (unsigned)(y0 + 1) < (unsigned)cs;
+      const float w00 = (inx0 && iny0) ? wx0 * wy0 : 0.0f, w01 = (inx1 && iny0) ? wx1 * wy0 : 0.0f;
+      const float w10 = (inx0 && iny1) ? wx0 * wy1 : 0.0f, w11 = (inx1 && iny1) ? wx1 * wy1 : 0.0f;
+      const float m = (w00 + w01) + (w10 + w11);
+      if (y0 + 1 < B.by0 || y0 >= B.by1 || x0 + 1 < B.bx0 || x0 >= B.bx1) {
+        r = padv.x * m; g = padv.y * m; b = padv.z * m;  // every neighbour is a pad pixel (or outside the canvas)
+      } else {
+        const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
+        const bool cy0 = y0 >= B.by0 && y0 < B.by1, cy1 = y0 + 1 >= B.by0 && y0 + 1 < B.by1;
+        const float4* row0 = fr + (int64_t)y0 * A.bw + x0;
+        const float4* row1 = row0 + A.bw;
+        const float4 v00 = (cx0 && cy0) ? __ldg(row0) : padv, v01 = (cx1 && cy0) ? __ldg(row0 + 1) : padv;
+        const float4 v10 = (cx0 && cy1) ? __ldg(row1) : padv, v11 = (cx1 && cy1) ? __ldg(row1 + 1) : padv;
+        r = fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00)));
+        g = fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00)));
+        b = fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00)));
+      }
+      r *= m;  // img * mask + (1 - mask) * 0
+      g *= m;
+      b *= m;
+    } else if (y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1) {
+      const float4 v = __ldg(fr + (int64_t)y * A.bw + x);
       r = v.x; g = v.y; b = v.z;
     } else {
-      r = padc[0]; g = padc[1]; b = padc[2];
+      r = padv.x; g = padv.y; b = padv.z;
     }
-  };
-  float r, g, b;
-  if (flags & NEXAR_AFFINE) {
-    const float xb = (float)x - (float)cs * 0.5f + 0.5f, yb = (float)y - (float)cs * 0.5f + 0.5f;
-    const float gx = __fadd_rn(__fadd_rn(__fmul_rn(xb, cp->grid[0]), __fmul_rn(yb, cp->grid[1])), cp->grid[2]);
-    const float gy = __fadd_rn(__fadd_rn(__fmul_rn(xb, cp->grid[3]), __fmul_rn(yb, cp->grid[4])), cp->grid[5]);
-    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)cs), 1.0f), 2.0f);
-    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)cs), 1.0f), 2.0f);
-    const float x0f = floorf(ix), y0f = floorf(iy);
-    const float wx1 = __fsub_rn(ix, x0f), wy1 = __fsub_rn(iy, y0f);
-    const float wx0 = __fsub_rn(1.0f, wx1), wy0 = __fsub_rn(1.0f, wy1);
-    // clamp before the int cast so wild matrices cannot overflow
-    const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)cs + 1.0f);
-    const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)cs + 1.0f);
-    r = g = b = 0.0f;
-    float m = 0.0f;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int xx = x0 + dx, yy = y0 + dy;
-        if (xx >= 0 && xx < cs && yy >= 0 && yy < cs) {
-          const float w = __fmul_rn(dx ? wx1 : wx0, dy ? wy1 : wy0);
-          float pr, pg, pb;
-          fetch(yy, xx, pr, pg, pb);
-          r = fmaf(pr, w, r);
-          g = fmaf(pg, w, g);
-          b = fmaf(pb, w, b);
-          m += w;
-        }
+    if (tail_fx) {
+      const int idx = y * cs + x;
+      if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+      if (flags & NEXAR_NOISE) {
+        const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
+        r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+        g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
+        b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
       }
-    r = __fmul_rn(r, m);  // img * mask + (1 - mask) * 0
-    g = __fmul_rn(g, m);
-    b = __fmul_rn(b, m);
-  } else {
-    fetch(y, x, r, g, b);
+      if (flags & NEXAR_BLUR) {
+        float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+        cv[idx] = r;
+        cv[cs * cs + idx] = g;
+        cv[2 * cs * cs + idx] = b;
+        continue;
+      }
+      point_effects(r, g, b, cp, flags, y, x);
+    }
+    const int64_t o = obase + (int64_t)y * A.sy;
+    if (A.normalize) {
+      r = fmaf(r, A.nscale[0], A.nbias[0]);
+      g = fmaf(g, A.nscale[1], A.nbias[1]);
+      b = fmaf(b, A.nscale[2], A.nbias[2]);
+    }
+    store_out<DstT>(A.dst, o, r);
+    store_out<DstT>(A.dst, o + A.sc, g);
+    store_out<DstT>(A.dst, o + 2 * A.sc, b);
   }
-  if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
-  if (flags & NEXAR_NOISE) {
-    const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
-    r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
-    g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
-    b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
-  }
-  if (flags & NEXAR_BLUR) {
-    float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
-    cv[idx] = r;
-    cv[cs * cs + idx] = g;
-    cv[2 * cs * cs + idx] = b;
-    return;
-  }
-  point_effects(r, g, b, cp, flags, y, x);
-  const int64_t o = (int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)y * A.sy + (int64_t)x * A.sx;
-  if (A.normalize) {
-    r = fmaf(r, A.nscale[0], A.nbias[0]);
-    g = fmaf(g, A.nscale[1], A.nbias[1]);
-    b = fmaf(b, A.nscale[2], A.nbias[2]);
-  }
-  store_out<DstT>(A.dst, o, r);
-  store_out<DstT>(A.dst, o + A.sc, g);
-  store_out<DstT>(A.dst, o + 2 * A.sc, b);
 }
 
 // K4: gaussian blur (tv gaussian_blur: reflect pad, outer-product kernel) + rest of the chain.
@@ -1217,8 +1266,8 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   }
   if (aug_mode) {
     const int cs = P.cs;
-    colour_kernel<<<dim3((K.bh * K.bw + 255) / 256, nf), 256, 0, st>>>(P, K, nbands);
-    geometry_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K, nbands);
+    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K, nbands);
+    geometry_kernel<DstT><<<dim3((cs + 31) / 32, (cs + 31) / 32, nf), 256, 0, st>>>(P, K);
     g_launches += 2;
     if (blur_mode) {
       blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
@@ -1243,6 +1292,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   const size_t esz = p->src_dtype == NEXAR_SRC_U8 ? 1 : 4;
   if (a->src_row_stride < (int64_t)(p->g.src_w * 3 * esz)) return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
 
+  if ((int64_t)a->n_clips * a->frames_per_clip > 65535) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: more than 65535 frames per call");
   Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace);
   KArgs K;
   K.src = a->src;
@@ -1264,6 +1314,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   }
   K.clip_max = w.clip_max;
   K.gray_partial = w.gray_partial;
+  K.pad_colour = w.pad_colour;
   K.inter = w.inter;
   K.canvas = w.canvas;
   K.n_frames = a->n_clips * a->frames_per_clip;
