@@ -1,0 +1,134 @@
+"""GPU tests of the callers either side of the kernel: Dataset mirror + GpuAugLoader (drop-in consumer line),
+inference windowing (cfg4 semantics), host-buffer pipeline (the e2e path of bench.py)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_sampler_oracle as S
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_AFTER = 1e-3
+
+
+class _FakeReader:
+    def __init__(self, n, seed, h=96, w=160):
+        from vision_collision_detection_b200.synth import make_clip_np
+        self.frames = make_clip_np(n, h, w, seed, "dashcam")
+
+    def __len__(self):
+        return len(self.frames)
+
+    def get_batch(self, idx):
+        return self.frames[list(idx)]
+
+
+def _rows():
+    return [{"id": f"v{i}", "video_type": "Normal", "path": f"{n}_{i}"} for i, n in enumerate([80, 30, 0, 64])]
+
+
+def _decoder(path):
+    n, seed = map(int, path.split("_"))
+    if n == 0:
+        raise IOError("broken video")
+    return _FakeReader(n, seed)
+
+
+def test_dataset_loader_drop_in_matches_oracle():
+    from torch.utils.data import DataLoader
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.videos import GpuAugLoader, GpuDashcamDataset, deferred_collate
+    kw = dict(mode="train", crop_size=56, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = create_video_transforms(**kw)
+    ds = GpuDashcamDataset(_rows(), fps=4, duration=3, transform=tf, sample_strategy="random", decoder=_decoder, defer=True)
+    random.seed(99)
+    loader = GpuAugLoader(DataLoader(ds, batch_size=4, shuffle=False, num_workers=0, collate_fn=deferred_collate), tf)
+    batch = next(iter(loader))
+    frames = batch["frames"]
+    assert tuple(frames.shape) == (4, 12, 56, 56, 3) and frames.is_cuda
+    dev = frames.device
+    x = batch["frames"].permute(0, 4, 1, 2, 3).float().to(dev)       # the trainers' consumer line (dvc:708)
+    assert x.is_contiguous() and x.data_ptr() == frames.data_ptr()     # pure view chain, no copy
+    assert torch.all(x[2] == 0)                                        # failed item -> all-zeros clip
+    # same draws on the oracle
+    cfg = O.TransformConfig(mode="train", crop_size=56, enable_custom_augmentation=True,
+                            aug=O.AugConfig(rotation_range=(-5, 5)))
+    random.seed(99)
+    for i, row in enumerate(_rows()):
+        n, seed = map(int, row["path"].split("_"))
+        if n == 0:
+            continue
+        start = S.start_frame(n, 12, "random", random)
+        idx = S.window_indices(n, 12, start)
+        clip = _FakeReader(n, seed).frames[idx]
+        want = O.clip_transform(clip.transpose(3, 0, 1, 2), cfg, random)
+        assert np.abs(x[i].cpu().numpy() - want).max() <= TOL_AFTER, i
+
+
+def test_dataset_with_transform_is_reference_shaped():
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.videos import GpuDashcamDataset
+    tf = create_video_transforms(mode="val", crop_size=56)
+    ds = GpuDashcamDataset(_rows(), fps=4, duration=3, is_train=False, transform=tf, sample_strategy="center",
+                           decoder=_decoder)
+    item = ds[0]
+    assert tuple(item["frames"].shape) == (12, 56, 56, 3) and item["frames"].dtype == torch.float32
+    assert tuple(item["sensor"].shape) == (12, 4) and item["target"] == "Normal" and item["id"] == "v0"
+    clip = _FakeReader(80, 0).frames[S.window_indices(80, 12, S.start_frame(80, 12, "center"))]
+    want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), O.TransformConfig(mode="val", crop_size=56),
+                                  {"flip": False, "aug": None})
+    assert np.abs(item["frames"].permute(3, 0, 1, 2).cpu().numpy() - want).max() <= TOL_AFTER
+    bad = ds[2]                     # decode failure -> zeros [T,224,224,3] like nexar_videos.py:479-489
+    assert tuple(bad["frames"].shape) == (12, 224, 224, 3) and float(bad["frames"].abs().sum()) == 0.0
+
+
+def test_sliding_windows_view_and_materialised():
+    from vision_collision_detection_b200.inference import SlidingWindowTransform, center_window, sliding_window_starts
+    from vision_collision_detection_b200.synth import make_clip_torch
+    video = make_clip_torch(1200, 48, 80, 5, "dashcam")              # 40 s x 30 fps (small frames)
+    for stride, k in ((16, 75), (8, 149)):
+        sw = SlidingWindowTransform(window=16, stride=stride, out_dtype=torch.float32)
+        view = sw.windows(video)
+        shape, nbytes = tuple(view.shape), view.untyped_storage().nbytes()
+        assert shape == (k, 3, 16, 224, 224)
+        assert nbytes == 1200 * 3 * 224 * 224 * 4          # zero copy: the storage is the per-frame result
+        starts = sliding_window_starts(1200, 16, stride)
+        for w in (0, k // 2, k - 1):
+            direct = sw.tf.forward_batch(video[starts[w]:starts[w] + 16].unsqueeze(0), out_dtype=torch.float32)[0]
+            same = bool(torch.equal(view[w], direct))
+            assert same, (stride, w)
+    sw = SlidingWindowTransform(window=16, stride=8, out_dtype=torch.float32)
+    same = bool(torch.equal(sw.windows(video[:200], materialize=True), sw.windows(video[:200]).contiguous()))
+    assert same
+    short = sw.windows(video[:10])                                      # shorter than a window: last frame repeated
+    shape, same = tuple(short.shape), bool(torch.equal(short[0, :, 9], short[0, :, 15]))
+    assert shape == (1, 3, 16, 224, 224) and same
+    cw = center_window(video, fps=10, duration=5)
+    assert tuple(cw.shape) == (1, 3, 50, 224, 224)
+    idx = S.window_indices(1200, 50, S.start_frame(1200, 50, "center"))
+    want = O.apply_clip_transform(video[idx[:2]].cpu().numpy().transpose(3, 0, 1, 2), O.TransformConfig(mode="val"),
+                                  {"flip": False, "aug": None})
+    assert np.abs(cw[0, :, :2].cpu().numpy() - want).max() <= TOL_AFTER
+
+
+def test_host_pipeline_equals_device_path():
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.host_pipeline import HostClipPipeline
+    from vision_collision_detection_b200.synth import make_clip_np
+    kw = dict(mode="train", crop_size=56, enable_custom_augmentation=True)
+    tf = create_video_transforms(**kw, out_dtype=torch.bfloat16)
+    clips = np.stack([make_clip_np(4, 96, 160, s, "dashcam") for s in range(7)])
+    random.seed(5)
+    params = tf.sample_params(7, 96, 160)
+    pipe = HostClipPipeline(tf, n_clips=7, frames=4, height=96, width=160, clips_per_chunk=2, n_streams=3)
+    host_in = pipe.pinned_input()
+    host_in.copy_(torch.from_numpy(clips))
+    got = pipe.run(host_in, params=params).clone()
+    want = tf.forward_batch(torch.from_numpy(clips).cuda(), params=params).cpu()
+    same = bool(torch.equal(got, want))
+    assert got.dtype == torch.bfloat16 and same
+    same = bool(torch.equal(pipe.run(host_in, params=params), want))  # buffers are reusable
+    assert same

@@ -1,0 +1,182 @@
+"""CPU-only tests of the host side: C-ABI library exports, geometry / tap tables against the oracle,
+parameter sampling and packing, clip sampler, Dataset mirror plumbing.  No kernel is launched."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_sampler_oracle as S
+from oracle import np_oracle as O
+from vision_collision_detection_b200 import _lib, create_video_transforms
+from vision_collision_detection_b200 import params as PR
+from vision_collision_detection_b200 import videos as V
+from vision_collision_detection_b200.inference import sliding_window_starts
+
+from golden_util import META, case_names, load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nexar_clip_transform.h")).read()
+    names = set(re.findall(r"\b(nexar_[a-z0-9_]+)\s*\(", hdr))
+    assert {"nexar_clip_transform", "nexar_plan_create", "nexar_workspace_bytes", "nexar_aa_taps"} <= names
+    L = _lib.lib()
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+    assert L.nexar_abi_version() == _lib.NEXAR_ABI_VERSION
+    assert L.nexar_sizeof_clip_params() == _lib.CLIP_PARAMS_DTYPE.itemsize
+    assert L.nexar_sizeof_transform_args() == ctypes.sizeof(_lib.TransformArgs)
+
+
+def test_geometry_matches_reference_table():
+    for key, (nh, nw, ph, pw) in META["geometry"].items():
+        hw, cs = key.split("->")
+        h, w = map(int, hw.split("x"))
+        g = _lib.letterbox_geometry(h, w, int(cs))
+        assert (g.resize_h, g.resize_w, g.off_y, g.off_x) == (nh, nw, ph, pw), key
+    g = _lib.resize_crop_geometry(96, 160, 56, 56)
+    assert (g.resize_h, g.resize_w, g.off_y, g.off_x) == (56, 93, 0, -18)
+    with pytest.raises(_lib.NexarError):
+        _lib.letterbox_geometry(0, 10, 8)
+
+
+@pytest.mark.parametrize("sizes", [(720, 125), (1280, 224), (1080, 126), (1920, 224), (720, 180), (40, 37),
+                                   (60, 56), (97, 47), (131, 64), (5, 5), (3, 9)])
+def test_tap_tables_bit_exact_with_oracle(sizes):
+    start, count, wts = _lib.aa_taps(*sizes)
+    xs, xc, xw = O.aa_taps(*sizes)
+    assert (start == xs).all() and (count == xc).all()
+    assert wts.shape == xw.shape and (wts == xw).all()
+    assert np.abs(wts.sum(axis=1) - 1.0).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", case_names("custom_small") + case_names("ncwv_small") + case_names("allfx_small")
+                         + case_names("poster_small") + ["train_portrait_flip"])
+def test_param_sampler_is_bit_exact_with_the_reference(name):
+    """R0: flip decision and every augmentation factor drawn from ``random`` equal the reference's."""
+    c = load_case(name)
+    tf = create_video_transforms(**c["kwargs"])
+    random.seed(c["random_seed"])
+    rec = tf.sample_params(1, 96, 160)[0]
+    assert rec["flip"] == c["params"]["flip"]
+    want = c["params"]["aug"]
+    if want is None:
+        assert rec["aug"] is None
+    else:
+        got = dict(rec["aug"])
+        if "cutout_boxes" in got:
+            got["cutout_boxes"] = [tuple(b) for b in got["cutout_boxes"]]
+        assert got == want
+
+
+def test_pack_clip_params_layout_and_errors():
+    aug = PR.VideoAugmentation(brightness_range=(0.9, 1.1), rotation_range=(-5, 5), cutout_prob=1.0,
+                               posterization_prob=1.0, blur_sigma=0.5, solarization_prob=1.0)
+    random.seed(3)
+    p = aug._sample_augmentation_parameters((3, 0, 56, 56))
+    packed, flags = PR.pack_clip_params([{"flip": True, "aug": p, "crop": (1, -2)}], 56, aug)
+    r = packed[0]
+    assert flags == int(r["flags"]) and flags & _lib.FLIP and flags & _lib.AUG and flags & _lib.AFFINE
+    assert flags & _lib.BLUR and r["blur_ksize"] == 5 and abs(r["blur_taps"][:5].sum() - 1) < 1e-6
+    assert (r["crop_dy"], r["crop_dx"]) == (1, -2)
+    assert r["brightness"] == np.float32(p["brightness"]) and r["contrast_q"] == np.float32(1.0 - p["contrast"])
+    m = O.inverse_affine_matrix(p["rotation"], [p["translate_x"], p["translate_y"]], p["scale"], [p["shear"], 0.0])
+    assert np.allclose(r["grid"], (np.asarray(m, np.float32) / np.float32(28.0)), rtol=0, atol=0)
+    assert r["n_cutout"] == len(p["cutout_boxes"]) and tuple(r["cutout"][0]) == tuple(p["cutout_boxes"][0])
+    bad = dict(p, hue=0.7)
+    with pytest.raises(ValueError):         # torchvision raises for |hue| > 0.5
+        PR.pack_clip_params([{"flip": False, "aug": bad}], 56, aug)
+    bad = dict(p, brightness=-0.1)
+    with pytest.raises(ValueError):
+        PR.pack_clip_params([{"flip": False, "aug": bad}], 56, aug)
+    # an un-augmented clip has no aug flags
+    packed, flags = PR.pack_clip_params([{"flip": False, "aug": None}], 56, None)
+    assert flags == 0 and packed[0]["flags"] == 0
+
+
+def test_factory_signature_matches_reference_kwargs():
+    """create_video_transforms accepts the reference's full kwarg surface (nexar_video_aug.py:636-696)."""
+    ref_kwargs = ["mode", "video_key", "num_samples", "convert_to_float", "crop_size", "normalize", "video_mean",
+                  "video_std", "min_size", "max_size", "horizontal_flip_prob", "enable_custom_augmentation",
+                  "aug_probability", "brightness_range", "contrast_range", "saturation_range", "hue_range",
+                  "rotation_range", "scale_range", "shear_range", "translate_range", "perspective_distortion",
+                  "noise_level", "blur_sigma", "jpeg_quality", "grayscale_prob", "cutout_prob", "cutout_count",
+                  "cutout_size_range", "color_inversion_prob", "solarization_prob", "posterization_prob",
+                  "posterization_bits_range", "solarization_threshold", "debug"]
+    import inspect
+    sig = list(inspect.signature(create_video_transforms).parameters)
+    assert sig[:len(ref_kwargs)] == ref_kwargs
+    tf = create_video_transforms(mode="train", enable_custom_augmentation=True, aug_probability=0.1)
+    assert tf.video_aug.aug_probability == 1.0      # dropped by the reference factory too (:762-788)
+    names = [getattr(t, "__name__", type(t).__name__) for t in tf.transforms]
+    assert names == ["letterbox_resize", "horizontal_flip", "VideoAugmentation", "normalize_tensor"]
+    assert [getattr(t, "__name__", "") for t in create_video_transforms(mode="val").transforms] == \
+        ["letterbox_resize", "normalize_tensor"]
+
+
+def test_clip_sampler_matches_oracle():
+    for n in [1, 10, 49, 50, 51, 120, 300, 1200]:
+        for st in ["random", "center", "metadata_time", "metadata_center", "uniform"]:
+            for ts, fps in [(None, 0.0), (3.7, 30.0), (0.1, 29.97), (38.0, 30.0)]:
+                random.seed(n * 7 + 3)
+                a = V.select_start_frame(n, 50, st, random, ts, fps)
+                random.seed(n * 7 + 3)
+                b = S.start_frame(n, 50, st, random, ts, fps)
+                assert a == b
+                assert V.window_indices(n, 50, a) == S.window_indices(n, 50, b)
+        assert V.uniform_indices(n, 16) == S.uniform_indices(n, 16)
+        assert V.model_frame_subsample(n) == S.model_subsample(n)
+    for s in (1, 8, 16):
+        assert sliding_window_starts(1200, 16, s) == S.sliding_window_starts(1200, 16, s)
+    assert sliding_window_starts(10, 16, 8) == [0]
+
+
+class _FakeReader:
+    def __init__(self, n, h=48, w=64):
+        self.frames = (np.arange(n * h * w * 3, dtype=np.int64) % 251).astype(np.uint8).reshape(n, h, w, 3)
+
+    def __len__(self):
+        return len(self.frames)
+
+    def get_batch(self, idx):
+        return self.frames[list(idx)]
+
+
+def test_deferred_dataset_and_collate_without_cuda():
+    rows = [{"id": "a", "video_type": "Normal", "path": "a.mp4"}, {"id": "b", "video_type": "Collision", "path": "b.mp4"},
+            {"id": "bad", "video_type": "Normal", "path": "missing.mp4"}]
+
+    def decoder(path):
+        if "missing" in path:
+            raise IOError("no such video")
+        return _FakeReader(30 if path.startswith("a") else 80)
+
+    tf = create_video_transforms(mode="train", crop_size=32)
+    ds = V.GpuDashcamDataset(rows, fps=10, duration=5, transform=tf, sample_strategy="center", decoder=decoder, defer=True)
+    assert len(ds) == 3
+    random.seed(0)
+    a, b, bad = ds[0], ds[1], ds[2]
+    assert tuple(a["frames_u8"].shape) == (50, 48, 64, 3) and a["frames_u8"].dtype == torch.uint8
+    assert torch.equal(a["frames_u8"][29], a["frames_u8"][49])           # short video: last frame repeated
+    assert torch.equal(b["frames_u8"][0], torch.from_numpy(_FakeReader(80).frames[15]))   # centre window start 40-25
+    assert bad["frames_u8"] is None                                      # any failure is swallowed
+    assert isinstance(a["params"]["flip"], bool)
+    batch = V.deferred_collate([a, b, bad])
+    assert tuple(batch["frames_u8"].shape) == (2, 50, 48, 64, 3) and batch["valid"] == [True, True, False]
+    assert batch["target"] == ["Normal", "Collision", "Normal"] and len(batch["params"]) == 2
+    assert list(V.shard_clips(10, 1, 4)) == [3, 4, 5] and list(V.shard_clips(10, 3, 4)) == [9]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vision_collision_detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

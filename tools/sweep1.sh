@@ -3,5 +3,5 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 B="python bench.py --steps 10 --warmup 3 --mode val --no-cpu-baseline --no-e2e"
-for nb in 1 3 5 8; do echo "bands=$nb"; NEXAR_FAST_BANDS=$nb $B 2>&1 | tail -1; done > gpurun_out/sweep_bands.log
-for v in build/*.so; do echo "lib=$v"; NEXAR_LIB=$PWD/$v $B 2>&1 | tail -1; done > gpurun_out/sweep_lib.log
+echo "default"; $B 2>&1 | tail -1
+for v in build/*.so; do echo "lib=$v"; NEXAR_LIB=$PWD/$v $B 2>&1 | tail -1; done

@@ -653,8 +653,18 @@ struct PairTable {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+#ifndef NEXAR_L1PF
+#define NEXAR_L1PF 0  // row pairs ahead of the register loads that are pulled into L1 (0 = off; measured: no gain)
+#endif
 __device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) {
+#if NEXAR_L1PF > 0
+  return __ldg((const uint4*)(base + off));
+#else
   return __ldcs((const uint4*)(base + off));
+#endif
+}
+__device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(base + off));
 }
 
 #ifndef NEXAR_MINB
@@ -787,6 +797,11 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     off = min(off + step, off_last); /* the tail re-reads the last pair */                                 \
     NA = ld_stream(frame_base, off);                                                                       \
     NB = ld_stream(frame_base, off + rs);                                                                  \
+    if (NEXAR_L1PF > 0) {                                                                                  \
+      const unsigned offp = min(off + (unsigned)NEXAR_L1PF * step, off_last);                              \
+      l1_prefetch(frame_base, offp);                                                                       \
+      l1_prefetch(frame_base, offp + rs);                                                                  \
+    }                                                                                                      \
     const uint4 e = TB.e[p];                                                                               \
     orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
     unsigned lo[4], hi[4];                                                                                 \

@@ -1,0 +1,66 @@
+"""Inference-time windowing on the device.
+
+``nexar_inference.py:211-231`` feeds the model one centred ``fps*duration`` window
+per video through the Dataset with ``create_video_transforms(mode='val')``;
+``center_window`` reproduces that.  The reference has no sliding-window code
+(SURVEY.md headline 7); ``SlidingWindowTransform`` is the extension BASELINE
+config 4 asks for: the val chain is per-frame and window-independent, so every
+frame of the video is transformed exactly once and the windows are strided views
+(or one gather when a materialised ``[K,3,T,cs,cs]`` batch is wanted).
+Window rule: starts ``k*stride`` for ``k = 0..floor((N-window)/stride)``; a video
+shorter than the window is padded by repeating its last frame (nexar_videos.py:429-433).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .video_aug import GpuVideoTransform, create_video_transforms
+from .videos import select_start_frame, window_indices
+
+
+def sliding_window_starts(num_frames: int, window: int, stride: int) -> List[int]:
+    if num_frames <= window:
+        return [0]
+    return [k * stride for k in range((num_frames - window) // stride + 1)]
+
+
+@torch.no_grad()
+def center_window(video_u8: torch.Tensor, transform: Optional[GpuVideoTransform] = None, fps: int = 10,
+                  duration: int = 5) -> torch.Tensor:
+    """[N,H,W,3] uint8 (device) -> [1,3,fps*duration,cs,cs]: sample_strategy='center' + val transform."""
+    tf = transform or create_video_transforms(mode="val")
+    n = video_u8.shape[0]
+    need = fps * duration
+    idx = window_indices(n, need, select_start_frame(n, need, "center"))
+    return tf.forward_batch(video_u8.unsqueeze(0), frame_index=torch.tensor([idx], dtype=torch.int64))
+
+
+class SlidingWindowTransform:
+    def __init__(self, window: int = 16, stride: int = 8, transform: Optional[GpuVideoTransform] = None,
+                 out_dtype: torch.dtype = torch.bfloat16):
+        self.window, self.stride = window, stride
+        self.tf = transform or create_video_transforms(mode="val", out_dtype=out_dtype)
+        self.out_dtype = out_dtype
+
+    @torch.no_grad()
+    def frames(self, video_u8: torch.Tensor) -> torch.Tensor:
+        """[N,H,W,3] uint8 on the device -> [N,3,cs,cs]: every frame transformed once."""
+        if video_u8.dim() != 4 or video_u8.shape[-1] != 3:
+            raise ValueError(f"expected [N,H,W,3], got {tuple(video_u8.shape)}")
+        n = video_u8.shape[0]
+        out = self.tf.forward_batch(video_u8.unsqueeze(0), layout="BTCHW", out_dtype=self.out_dtype)  # [1,N,3,cs,cs]
+        if n < self.window:       # pad by repeating the last frame
+            out = torch.cat([out, out[:, -1:].expand(1, self.window - n, *out.shape[2:])], dim=1)
+        return out[0]
+
+    def windows(self, video_u8: torch.Tensor, materialize: bool = False) -> torch.Tensor:
+        """-> [K,3,window,cs,cs].  A zero-copy strided view of the per-frame result unless ``materialize``."""
+        fr = self.frames(video_u8)                                   # [N',3,cs,cs]
+        starts = sliding_window_starts(fr.shape[0], self.window, self.stride)
+        k = len(starts)
+        s = fr.stride()
+        view = fr.as_strided((k, 3, self.window, fr.shape[2], fr.shape[3]),
+                             (self.stride * s[0], s[1], s[0], s[2], s[3]))
+        return view.contiguous() if materialize else view

@@ -1,0 +1,232 @@
+"""Clip sampler, Dataset mirror and GPU augmentation loader.
+
+Mirrors the tensor-shaping half of the reference Datasets
+(``NvidiaDashcamDataset`` nexar_videos.py:39-496, ``VideoDataset``
+nexar_complete_with_validation.py:57-234, the notebook's uniform sampler
+inference.ipynb cell 0) around the fused GPU transform:
+
+* ``select_start_frame`` / ``window_indices`` / ``uniform_indices`` — the integer
+  window rules, drawing from ``random`` exactly where the reference does.
+* ``GpuDashcamDataset`` — same constructor signature and ``__getitem__`` contract
+  (``{'frames': [T,cs,cs,3] f32, 'sensor': [T,4], 'target', 'id'}``, zeros on any
+  error).  Video decode is a pluggable callable (decord is the default when it is
+  installed; decode itself is outside this path).  With ``defer=True`` it returns
+  the raw uint8 window and the clip's random decisions instead, so that forked
+  DataLoader workers never touch CUDA.
+* ``GpuAugLoader`` — wraps a DataLoader over deferred items, copies each uint8
+  batch to the device and runs the fused kernel once per batch; yields batches
+  whose ``'frames'`` is a ``[B,T,cs,cs,3]`` view of the ``[B,3,T,cs,cs]`` result, so
+  the trainers' ``batch['frames'].permute(0,4,1,2,3).float().to(device)``
+  (distributed_video_classifier.py:708) is a no-op view chain.
+"""
+from __future__ import annotations
+
+import random
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .video_aug import GpuVideoTransform
+
+
+# ---------------------------------------------------------------------------------
+# R1: temporal window selection
+# ---------------------------------------------------------------------------------
+def select_start_frame(num_frames: int, frames_needed: int, strategy: str = "random", rng=random,
+                       timestamp_sec: Optional[float] = None, video_fps: float = 0.0) -> int:
+    """nexar_videos.py:364-415 (strategies 'random', 'center', 'metadata_time') and
+    nexar_complete_with_validation.py:126-155 ('metadata_center')."""
+    if strategy in ("metadata_time", "metadata_center"):
+        if timestamp_sec is not None and video_fps > 0:
+            start = max(0, int(timestamp_sec * video_fps) - frames_needed // 2)
+            if start + frames_needed > num_frames:
+                start = max(0, num_frames - frames_needed)
+        elif strategy == "metadata_time":
+            start = rng.randint(0, max(0, num_frames - frames_needed))
+        else:
+            start = rng.randint(0, num_frames - frames_needed) if num_frames > frames_needed else 0
+    elif strategy == "center":
+        start = 0
+        if num_frames > frames_needed:
+            start = max(0, num_frames // 2 - frames_needed // 2)
+            if start + frames_needed > num_frames:
+                start = max(0, num_frames - frames_needed)
+    else:   # 'random'; unknown strategies fall back to it (nexar_videos.py:57-58)
+        start = rng.randint(0, num_frames - frames_needed) if num_frames > frames_needed else 0
+    return max(0, min(start, num_frames - 1))
+
+
+def window_indices(num_frames: int, frames_needed: int, start: int) -> List[int]:
+    """nexar_videos.py:416-435: consecutive frames, the last one repeated when the video is short."""
+    idx = list(range(start, min(start + frames_needed, num_frames)))
+    if idx and len(idx) < frames_needed:
+        idx += [idx[-1]] * (frames_needed - len(idx))
+    return idx[:frames_needed]
+
+
+def uniform_indices(total_frames: int, num_frames: int) -> List[int]:
+    """inference.ipynb cell 0: wrap-pad short videos, else truncating linspace."""
+    if total_frames < num_frames:
+        idx = np.pad(np.arange(total_frames), (0, num_frames - total_frames), mode="wrap")
+    else:
+        idx = np.linspace(0, total_frames - 1, num_frames, dtype=int)
+    return [int(i) for i in idx]
+
+
+def model_frame_subsample(num_frames: int) -> List[int]:
+    """nexar_arch.py:411-415: the model keeps every other frame when T > 10."""
+    return list(range(0, num_frames, 2)) if num_frames > 10 else list(range(num_frames))
+
+
+# ---------------------------------------------------------------------------------
+# Dataset mirror
+# ---------------------------------------------------------------------------------
+def _decord_reader(path: str):
+    import decord  # not installed in every image; only needed when no decoder is injected
+    return decord.VideoReader(path, ctx=decord.cpu(0))
+
+
+def _to_uint8_array(frames) -> np.ndarray:
+    if hasattr(frames, "asnumpy"):
+        frames = frames.asnumpy()
+    elif isinstance(frames, torch.Tensor):
+        frames = frames.cpu().numpy()
+    return np.asarray(frames)
+
+
+class GpuDashcamDataset(Dataset):
+    """``NvidiaDashcamDataset(metadata_df, base_dirs, fps, duration, is_train, skip_missing, transform,
+    sample_strategy, sensor_subdir, time_column)`` work-alike for the frames path.  ``metadata_df`` may be a
+    pandas DataFrame or a list of dicts with 'id', 'video_type' and, optionally, 'path' / the time column.
+    IMU/sensor sync is out of scope: 'sensor' is the reference's zero fallback."""
+
+    def __init__(self, metadata_df, base_dirs=None, fps=10, duration=5, is_train=True, skip_missing=True,
+                 transform: Optional[GpuVideoTransform] = None, sample_strategy="random", sensor_subdir="signals",
+                 time_column=None, *, decoder: Optional[Callable[[str], Any]] = None,
+                 path_resolver: Optional[Callable[[str], Optional[str]]] = None, defer: bool = False,
+                 video_fps_lookup: Optional[Callable[[str], float]] = None):
+        rows = metadata_df.to_dict("records") if hasattr(metadata_df, "to_dict") else list(metadata_df)
+        self.fps, self.duration, self.is_train = fps, duration, is_train
+        self.transform = transform
+        self.sample_strategy = sample_strategy if sample_strategy in ("random", "metadata_time", "center") else "random"
+        if self.sample_strategy == "metadata_time" and (time_column is None or not rows or time_column not in rows[0]):
+            self.sample_strategy = "random"
+        self.time_column = time_column
+        self.base_dirs = base_dirs if isinstance(base_dirs, (list, tuple)) else [base_dirs]
+        self.decoder = decoder or _decord_reader
+        self.defer = defer
+        self.video_fps_lookup = video_fps_lookup
+        import os
+        self.rows, self.video_paths = [], []
+        for row in rows:
+            path = row.get("path")
+            if path is None and path_resolver is not None:
+                path = path_resolver(row["id"])
+            if path is None and self.base_dirs[0] is not None:
+                for base in self.base_dirs:
+                    cand = os.path.join(base, str(row["id"]), f"{row['id']}.mp4")
+                    if os.path.exists(cand):
+                        path = cand
+                        break
+                if path is None and not skip_missing:
+                    path = os.path.join(self.base_dirs[0], str(row["id"]), f"{row['id']}.mp4")
+            if path is None and skip_missing:
+                continue
+            self.rows.append(row)
+            self.video_paths.append(path)
+
+    def __len__(self):
+        return len(self.video_paths)
+
+    def _window(self, reader, row, idx) -> List[int]:
+        n = len(reader)
+        need = self.fps * self.duration
+        ts, vfps = None, 0.0
+        if self.sample_strategy == "metadata_time":
+            ts = row.get(self.time_column)
+            vfps = self.video_fps_lookup(self.video_paths[idx]) if self.video_fps_lookup else 30.0
+        start = select_start_frame(n, need, self.sample_strategy, random, ts, vfps)
+        return window_indices(n, need, start)
+
+    def __getitem__(self, idx):
+        row = self.rows[idx]
+        need = self.fps * self.duration
+        target, vid = row.get("video_type"), row.get("id")
+        try:
+            reader = self.decoder(self.video_paths[idx])
+            indices = self._window(reader, row, idx)
+            frames = _to_uint8_array(reader.get_batch(indices))
+            if len(frames) < need:          # nexar_videos.py:429-433
+                last = frames[-1] if len(frames) else np.zeros(frames.shape[1:] or (720, 1280, 3), np.uint8)
+                frames = np.concatenate([frames, np.repeat(last[None], need - len(frames), axis=0)], axis=0)
+            frames = torch.from_numpy(np.ascontiguousarray(frames[:need]))
+            if self.defer:
+                t = self.transform
+                params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
+                return {"frames_u8": frames, "params": params, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+            video = frames.permute(3, 0, 1, 2)                  # nexar_videos.py:441
+            video = self.transform(video) if self.transform else video.float() / 255.0
+            frames = video.permute(1, 2, 3, 0)                  # nexar_videos.py:451
+        except Exception:
+            # nexar_videos.py:479-489: swallow everything, return an all-zeros clip of the standard size
+            size = (224, 224) if self.transform else (720, 1280)
+            if self.defer:
+                return {"frames_u8": None, "params": None, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+            frames = torch.zeros(need, size[0], size[1], 3)
+        return {"frames": frames, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+
+
+def deferred_collate(items: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
+    """collate_fn for ``defer=True`` datasets: stacks what stacks, keeps params / failures as lists."""
+    ok = [it["frames_u8"] is not None for it in items]
+    good = [it["frames_u8"] for it, k in zip(items, ok) if k]
+    return {
+        "frames_u8": torch.stack(good) if good else None,
+        "valid": ok,
+        "params": [it["params"] for it, k in zip(items, ok) if k],
+        "sensor": torch.stack([it["sensor"] for it in items]),
+        "target": [it["target"] for it in items],
+        "id": [it["id"] for it in items],
+    }
+
+
+class GpuAugLoader:
+    """Iterates a DataLoader of deferred batches and runs the fused transform on the device, once per batch."""
+
+    def __init__(self, loader: Iterable, transform: GpuVideoTransform, device=None, out_dtype: Optional[torch.dtype] = None):
+        self.loader, self.transform = loader, transform
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.out_dtype = out_dtype
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        tf = self.transform
+        cs = tf.crop_size
+        for batch in self.loader:
+            valid = batch["valid"]
+            n = len(valid)
+            out = None
+            if batch["frames_u8"] is not None:
+                u8 = batch["frames_u8"].to(self.device, non_blocking=True)
+                params = batch["params"] if all(p is not None for p in batch["params"]) else None
+                res = tf.forward_batch(u8, params=params, out_dtype=self.out_dtype)       # [b,3,T,cs,cs]
+                if all(valid):
+                    out = res
+                else:   # failed items become the reference's all-zeros clip (nexar_videos.py:479-489)
+                    out = torch.zeros((n,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
+                    out[torch.tensor(valid, device=self.device)] = res
+            else:
+                t = batch["sensor"].shape[1]
+                out = torch.zeros((n, 3, t, cs, cs), dtype=self.out_dtype or tf.out_dtype, device=self.device)
+            yield {"frames": out.permute(0, 2, 3, 4, 1), "sensor": batch["sensor"], "target": batch["target"],
+                   "id": batch["id"]}
+
+
+def shard_clips(n_clips: int, rank: int, world: int) -> range:
+    """Contiguous split of a batch over ranks: clips are independent, no collective."""
+    per = (n_clips + world - 1) // world
+    return range(min(n_clips, rank * per), min(n_clips, (rank + 1) * per))
