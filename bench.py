@@ -46,6 +46,16 @@ def algorithmic_bytes_per_clip(t, h, w, cs, out_bytes):
     return t * h * w * 3 + 3 * t * cs * cs * out_bytes
 
 
+def ncu_traffic(mode):
+    """dram bytes per launch of the resize kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(mode)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -158,14 +168,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="custom", choices=sorted(KW))
     ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--ref-clips", type=int, default=4, help="clips per step for --impl reference")
-    ap.add_argument("--cpu-clips", type=int, default=8, help="clips for the cpu_baseline leg")
+    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step for --impl reference")
+    ap.add_argument("--cpu-clips", type=int, default=64, help="clips for the cpu_baseline leg (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -244,7 +254,7 @@ def main():
         pipe = HostClipPipeline(tf, n_clips=b, frames=t, height=h, width=w, device=dev)
         host_in = pipe.pinned_input()
         host_in.copy_(clips.cpu())
-        e2e_steps = max(3, min(args.steps, 6))
+        e2e_steps = max(3, min(args.steps, 8))
         for i in range(2):
             pipe.run(host_in, params=param_sets[i % len(param_sets)])
         barrier()
@@ -276,7 +286,7 @@ def main():
             roof = {"bound": "hbm", "kernel": "resize (K1)", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "frac_of_8TBs_nominal": ach / 8000.0, "peak_kind": peak_kind,
                     "kernel_ms": k1_ms_avg, "kernel_share_of_step": k1_ms_avg / ms_step,
-                    "algorithmic_bytes_per_launch": k1_bytes, "traffic": None,
+                    "algorithmic_bytes_per_launch": k1_bytes, "traffic": ncu_traffic(args.mode),
                     "step_achieved_GBs": b * per_clip / (ms_step * 1e-3) / 1e9}
         cpu = None
         if not args.no_cpu_baseline:

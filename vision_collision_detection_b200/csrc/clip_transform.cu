@@ -1244,7 +1244,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB); else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB); else NEXAR_FAST(20, 256, 2);
     } else {
-      if (kx == 10) NEXAR_FAST(10, 384, 1); else if (kx == 14) NEXAR_FAST(14, 384, 1); else NEXAR_FAST(20, 384, 1);
+      if (kx == 10) NEXAR_FAST(10, 384, 2); else if (kx == 14) NEXAR_FAST(14, 384, 2); else NEXAR_FAST(20, 384, 2);
     }
 #undef NEXAR_FAST
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
