@@ -82,8 +82,8 @@ struct NexarPlan {
 // down-scale keeps at most two output rows alive at any source row (ymin[i+2] >= ymax[i]), so two
 // rotating accumulator slots suffice (out row i lives in slot i % 2).  The kernel consumes source rows
 // in PAIRS through dp2a; table entry p = {w slot0, w slot1, w post, emit} with w = u16x2 (row 2p | row
-// 2p+1 << 16), emit = bit0 (an output row's last tap lies in this pair) | slot << 1 | begin0 << 2 |
-// begin1 << 3 (the slot's accumulators restart at this pair) | out_row << 4, and "w post" the first tap of the NEXT row of that slot when it falls in the same pair (it is
+// 2p+1 << 16), z = bit0 (an output row's last tap lies in this pair) | slot << 1 | begin0 << 2 |
+// begin1 << 3 (the slot's accumulators restart at this pair) | out_row << 4 | post tap << 16, and "w post" the first tap of the NEXT row of that slot when it falls in the same pair (it is
 // accumulated after the finished row has been flushed).  Returns false when the geometry does not fit.
 static const int kMaxPairs = 1024;
 static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
@@ -127,22 +127,28 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
       const int y = ys + k;
       uint4& e = p->pairs[y / 2];
       if (prev_last >= 0 && prev_last / 2 == y / 2) {
-        if (!(y & 1) || e.z) return false;
-        e.z = (unsigned)q[k] << 16;  // accumulated with "begin" semantics after the flush
+        if (!(y & 1) || e.w) return false;
+        e.w = (unsigned)q[k] << 16;  // accumulated with "begin" semantics after the flush (temporarily in .w)
         if (q[k]) begun = true;
       } else {
         unsigned& ws = slot ? e.y : e.x;
         if (!begun && q[k]) {  // first non-zero tap of the row: the accumulators restart from the rounding constant
           if (ws) return false;
-          e.w |= slot ? 8u : 4u;
+          e.z |= slot ? 8u : 4u;
           begun = true;
         }
         ws |= (unsigned)q[k] << (16 * (y & 1));
       }
     }
-    unsigned& em = p->pairs[(ys + yc - 1) / 2].w;
+    unsigned& em = p->pairs[(ys + yc - 1) / 2].z;
     if (em & 1u) return false;  // one flush per pair
+    if (i >= 4096) return false;
     em |= 1u | ((unsigned)slot << 1) | ((unsigned)i << 4);
+  }
+  for (uint4& e : p->pairs) {  // final packing: z = post tap << 16 | out_row << 4 | flags, w unused
+    if (e.w && !(e.z & 1u)) return false;
+    e.z = (e.z & 0xFFFFu) | e.w;
+    e.w = 0u;
   }
   p->xstart_al.assign(g.resize_w, 0);
   p->xwt_al.assign((size_t)g.resize_w * kx_al, 0.f);
@@ -375,7 +381,6 @@ static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
 static const int kMaxBands = 16;
-struct PairTable;
 
 
 struct Workspace {
@@ -634,8 +639,8 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 // pair ahead in registers (ping-pong), while warp 0 pushes the rows LOOKAHEAD pairs ahead into L2
 // through the bulk-copy engine (cp.async.bulk.prefetch.L2).  The two rows' bytes are interleaved
 // with PRMT and fed to dp2a against the 16-bit fixed-point taps of the (at most two) output rows
-// alive at that height.  The tap table lives in the kernel parameters (constant bank), so the
-// per-pair control flow is uniform.  A finished row is rounded to 15-bit fixed point (value*128),
+// alive at that height.  The per-pair control words (taps, begin/flush flags) are read one pair
+// ahead, so no branch waits on its own load.  A finished row is rounded to 15-bit fixed point (value*128),
 // staged in shared memory (double buffered: one __syncthreads per output row) and resampled
 // horizontally in fp32, one output pixel per thread with its taps in registers.  The uint16 ->
 // float conversion is a single PRMT that builds the float 2^15 + v; the constant 2^15 * sum(w) is
@@ -645,10 +650,6 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ float magic_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4105)); }
 __device__ __forceinline__ float magic_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4325)); }
-
-struct PairTable {
-  uint4 e[kMaxPairs];
-};
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -683,7 +684,7 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 
 template <int KX, int NT, int MINB, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
-resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, const __grid_constant__ PairTable TB) {
+resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
   constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine (multiple of 4)
@@ -731,9 +732,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
     const float post = scale * (1.0f / 128.0f);
-    // where this thread's pixel goes (row term added per output row)
-    const int64_t opix = dbase + (int64_t)xo * A.sx;
-    float4* ipix = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0);
+    // where this thread's pixel goes (row term added per output row): intermediate (augmented clips) or dst
+    char* const optr = aug ? (char*)(A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0))
+                           : (char*)A.dst + (dbase + (int64_t)xo * A.sx) * (int64_t)sizeof(DstT);
 
     // ---- vertical pass state ----
     const int sh = P.shift - 7;
@@ -750,11 +751,11 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const unsigned step = 2u * rs;
     const unsigned off_last = (unsigned)(2 * plast) * rs + (unsigned)chunk * 16u;
     unsigned off = (unsigned)(2 * p0) * rs + (unsigned)chunk * 16u;
-    unsigned sbuf = (unsigned)tid * 32u;  // byte offset of this thread's staging slot in the current buffer
-    unsigned hbuf = hbyte;
-    unsigned dlt = (unsigned)vstride * 2u;  // +-bytes to the other staging buffer
+    const unsigned vbytes = (unsigned)vstride * 2u;
+    unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
 
     uint4 a0 = ld_stream(frame_base, off), b0 = ld_stream(frame_base, off + rs);
+    uint4 e_nx = __ldg(P.pairs + p0);
     uint4 a1, b1;
     if (tid < 32) {
       const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
@@ -786,7 +787,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     _Pragma("unroll") for (int q = 0; q < 8; ++q)                                             \
         w_[q] = __byte_perm(ACC[2 * q] >> sh, ACC[2 * q + 1] << (16 - sh), 0x7610);           \
     if (vstore) {                                                                             \
-      uint4* d_ = (uint4*)(smem_raw + sbuf);                                                  \
+      uint4* d_ = (uint4*)(smem_raw + bufoff + (unsigned)tid * 32u);                          \
       d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                                         \
       d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
     }                                                                                         \
@@ -802,41 +803,45 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       l1_prefetch(frame_base, offp);                                                                       \
       l1_prefetch(frame_base, offp + rs);                                                                  \
     }                                                                                                      \
-    const uint4 e = TB.e[p];                                                                               \
+    const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
+    e_nx = __ldg(P.pairs + min(p + 1, plast)); /* control words of the next pair, one iteration ahead */   \
     orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
     unsigned lo[4], hi[4];                                                                                 \
     lo[0] = __byte_perm(CA.x, CB.x, 0x5140); hi[0] = __byte_perm(CA.x, CB.x, 0x7362);                      \
     lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
-    if (e.w == 0u) { /* common case: no row starts or ends in this pair */                                \
-      if (e.x) NEXAR_ACCUM(acc0, e.x)                                                                      \
-      if (e.y) NEXAR_ACCUM(acc1, e.y)                                                                      \
+    if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
+      if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
+      if (ey) NEXAR_ACCUM(acc1, ey)                                                                      \
     } else {                                                                                               \
-      if (e.x) {                                                                                           \
-        if (e.w & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, e.x) else NEXAR_ACCUM(acc0, e.x)                 \
+      if (ex) {                                                                                           \
+        if (ez & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, ex) else NEXAR_ACCUM(acc0, ex)                 \
       }                                                                                                    \
-      if (e.y) {                                                                                           \
-        if (e.w & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, e.y) else NEXAR_ACCUM(acc1, e.y)                 \
+      if (ey) {                                                                                           \
+        if (ez & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, ey) else NEXAR_ACCUM(acc1, ey)                 \
       }                                                                                                    \
     }                                                                                                      \
-    if (e.w & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
-      const int row = (int)(e.w >> NEXAR_E_ROWSHIFT);                                                      \
-      const bool s1 = (e.w & NEXAR_E_SLOT) != 0u;                                                          \
+    if (ez & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
+      const int row = (int)((ez >> NEXAR_E_ROWSHIFT) & 0xFFFu);                                                      \
+      const bool s1 = (ez & NEXAR_E_SLOT) != 0u;                                                          \
       if (row >= i0 && row < i1) {                                                                         \
         if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
         __syncthreads();                                                                                   \
         if (hth) {                                                                                         \
-          const unsigned* src = (const unsigned*)(smem_raw + hbuf);                                        \
+          const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
           float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
+          unsigned w0 = src[0], w1 = src[1], w2 = src[2];                                                  \
           _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
-            const unsigned w0 = src[3 * (k >> 1)], w1 = src[3 * (k >> 1) + 1], w2 = src[3 * (k >> 1) + 2]; \
+            unsigned n0 = 0u, n1 = 0u, n2 = 0u;                                                            \
+            if (k + 2 < KX) { n0 = src[3 * (k >> 1) + 3]; n1 = src[3 * (k >> 1) + 4]; n2 = src[3 * (k >> 1) + 5]; } \
             r = fmaf(wx[k], magic_lo(w0), r);                                                              \
             g = fmaf(wx[k], magic_hi(w0), g);                                                              \
             bl = fmaf(wx[k], magic_lo(w1), bl);                                                            \
             r = fmaf(wx[k + 1], magic_hi(w1), r);                                                          \
             g = fmaf(wx[k + 1], magic_lo(w2), g);                                                          \
             bl = fmaf(wx[k + 1], magic_hi(w2), bl);                                                        \
+            w0 = n0; w1 = n1; w2 = n2;                                                                     \
           }                                                                                                \
           r = (r - hbias) * post;                                                                          \
           g = (g - hbias) * post;                                                                          \
@@ -848,23 +853,24 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
             g = clamp01(__fmul_rn(bright, g));                                                             \
             bl = clamp01(__fmul_rn(bright, bl));                                                           \
             gsum += gray_of(r, g, bl);                                                                     \
-            ipix[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                                          \
+            ((float4*)optr)[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                              \
           } else {                                                                                         \
-            const int64_t o = opix + (int64_t)y * A.sy;                                                    \
+            DstT* const o = (DstT*)optr + (int64_t)y * A.sy;                                               \
             if (A.normalize) {                                                                             \
               r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
               g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
               bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
             }                                                                                              \
-            store_out<DstT>(A.dst, o, r);                                                                  \
-            store_out<DstT>(A.dst, o + A.sc, g);                                                           \
-            store_out<DstT>(A.dst, o + 2 * A.sc, bl);                                                      \
+            store_out<DstT>(o, 0, r);                                                                      \
+            store_out<DstT>(o, A.sc, g);                                                                   \
+            store_out<DstT>(o, 2 * A.sc, bl);                                                              \
           }                                                                                                \
         }                                                                                                  \
-        sbuf += dlt; hbuf += dlt; dlt = 0u - dlt; /* other staging buffer */                                \
+        bufoff = vbytes - bufoff; /* other staging buffer */                                               \
       }                                                                                                    \
-      if (e.z) { /* first tap of the slot's next row shares this pair */                                   \
-        if (s1) NEXAR_ACCUM_BEGIN(acc1, e.z) else NEXAR_ACCUM_BEGIN(acc0, e.z)                             \
+      const unsigned wpost = ez & 0xFFFF0000u;                                                             \
+      if (wpost) { /* first tap of the slot's next row shares this pair */                                 \
+        if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                         \
       }                                                                                                    \
     }                                                                                                      \
     if ((p & 3) == 3 && tid < 32) { /* warp 0: next 4 pairs, LA ahead, into L2 */                          \
@@ -1210,8 +1216,6 @@ __global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
   store_out<DstT>(A.dst, o + 2 * A.sc, b);
 }
 
-static thread_local PairTable g_pair_table;
-
 // ---------------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------------
@@ -1235,12 +1239,9 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const int kx = P.kx_al;
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
-    PairTable* tb = &g_pair_table;  // host staging of the kernel-parameter tap table
-    memset(tb, 0, sizeof(PairTable));
-    memcpy(tb->e, p->pairs.data(), p->pairs.size() * sizeof(uint4));
     K.pass = 0;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
-#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K, *tb)
+#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K)
     if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB); else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB); else NEXAR_FAST(20, 256, 2);
     } else {
