@@ -191,9 +191,12 @@ def test_fast_and_general_resize_kernels_agree(name, bands):
         L.nexar_set_resize_kernel(0)
         L.nexar_set_fast_bands(bands)
         fast = _run(_tf(c["kwargs"]), c["clip"], c["params"])
+        L.nexar_set_resize_kernel(3)            # TMA-ring variant: same arithmetic, bulk-copy staging
+        tma = _run(_tf(c["kwargs"]), c["clip"], c["params"])
     finally:
         L.nexar_set_resize_kernel(0)
         L.nexar_set_fast_bands(0)
     assert np.abs(general - c["out"]).max() <= tol
     assert np.abs(fast - c["out"]).max() <= tol
     assert np.abs(fast - general).max() <= 2.5e-4      # fixed-point budget: < 3e-5 of full scale, /0.225
+    assert np.array_equal(tma, fast)

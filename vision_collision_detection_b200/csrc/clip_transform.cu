@@ -27,7 +27,7 @@
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-static int g_resize_variant = 0;  // 0 auto, 1 force the general kernel
+static int g_resize_variant = 0;  // 0 auto (register-prefetch fast kernel), 1 force the general kernel, 3 TMA-ring fast kernel
 static int g_fast_bands = 0;      // 0 auto
 
 static std::vector<cudaEvent_t> g_prof_ev;
@@ -501,6 +501,44 @@ __device__ __forceinline__ Box clip_box(const DevPlan& P, int crop_dy, int crop_
   return b;
 }
 
+
+// Constant fill of the canvas rows/columns outside a band's content box (the normalised value of a
+// zero pixel).  Whole pad rows of a planar layout go out as 16-byte stores.
+template <typename DstT, int NT>
+__device__ __forceinline__ void fill_pads(const DevPlan& P, const KArgs& A, const Box& B, int64_t dbase, int band, int nb,
+                                          int i0, int i1, int tid) {
+  const int Y0 = band == 0 ? 0 : i0 + B.oy;
+  const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
+  const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;
+  float nbi[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
+  constexpr int EPV = 16 / (int)sizeof(DstT);  // elements per 16-byte store
+  const bool vec_ok = A.sx == 1 && (P.cs % EPV) == 0 && (A.sy % EPV) == 0 && (A.sc % EPV) == 0 && (A.st % EPV) == 0 &&
+                      (A.sb % EPV) == 0 && (((uintptr_t)A.dst) & 15) == 0;
+  for (int y = Y0; y < Y1; ++y) {
+    const bool content_row = (y >= cy0 && y < cy1) && B.bx1 > B.bx0;
+    if (!content_row && vec_ok) {
+      const int nvec = P.cs / EPV;
+      for (int v = tid; v < 3 * nvec; v += NT) {
+        const int c = v / nvec, xv = v - c * nvec;
+        DstT tmp[EPV];
+#pragma unroll
+        for (int k = 0; k < EPV; ++k) store_out<DstT>(tmp, k, nbi[c]);
+        DstT* d = (DstT*)A.dst + dbase + (int64_t)y * A.sy + (int64_t)c * A.sc + (int64_t)xv * EPV;
+        *(uint4*)d = *(const uint4*)tmp;
+      }
+      continue;
+    }
+    for (int x = tid; x < P.cs; x += NT) {
+      if (content_row && x >= B.bx0 && x < B.bx1) continue;
+      const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // K0: clip maximum (only for crop geometries, where K1 does not read every source pixel)
 // ---------------------------------------------------------------------------------
@@ -670,6 +708,9 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 
 #ifndef NEXAR_MINB
 #define NEXAR_MINB 3
+#endif
+#ifndef NEXAR_STAGES
+#define NEXAR_STAGES 6  // row pairs in flight per CTA in the TMA ring
 #endif
 #ifndef NEXAR_LOOKAHEAD
 #define NEXAR_LOOKAHEAD 12
@@ -893,23 +934,275 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
 #undef NEXAR_STAGE
   }
 
-  if (!aug) {
-    const int Y0 = band == 0 ? 0 : i0 + B.oy;
-    const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
-    const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;
-    float nbi[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
-    for (int y = Y0; y < Y1; ++y) {
-      const bool content_row = (y >= cy0 && y < cy1);
-      for (int x = tid; x < P.cs; x += NT) {
-        if (content_row && x >= B.bx0 && x < B.bx1) continue;
-        const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
-      }
-    }
+  if (!aug) fill_pads<DstT, NT>(P, A, B, dbase, band, nb, i0, i1, tid);
+  if (A.pass == 0) {
+    const bool big = (orv & 0xFEFEFEFEu) != 0u;
+    if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
   }
+  if (aug) {
+    const float s = block_sum(gsum, red);
+    if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
+  }
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// K1 (TMA variant): same arithmetic as resize_fast_kernel, but the source rows arrive through an
+// NS-stage shared-memory ring filled by 1-D bulk copies (one row pair = one contiguous copy) that thread 0
+// issues and mbarriers track; every warp releases a stage as soon as its bytes are in registers.  No
+// per-thread global address arithmetic, no register prefetch, no L2 prefetch.
+template <int KX, int NT, int MINB, int NS, typename DstT>
+__global__ void __launch_bounds__(NT, MINB)
+resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[32];
+    const int tid = threadIdx.x;
+  const int frame = blockIdx.y;
+  const int clip = frame / A.T;
+  const int t = frame - clip * A.T;
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  float scale;
+  if (A.pass == 0) {
+    scale = 1.0f / 255.0f;
+  } else {
+    const bool big = A.clip_max[clip] != 0u;
+    if (A.pass == 1 && big) return;
+    scale = big ? 1.0f / 255.0f : 1.0f;
+  }
+  const bool flip = flags & NEXAR_FLIP, aug = flags & NEXAR_AUG;
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flip);
+  const int nb = gridDim.x, band = blockIdx.x;
+  const int per = (B.i_hi - B.i_lo + nb - 1) / nb;
+  const int i0 = min(B.i_hi, B.i_lo + band * per), i1 = min(B.i_hi, i0 + per);
+  const int W3 = P.src_w * 3;
+  const int nchunks = W3 >> 4;
+  const int vstride = (W3 + KX * 3 + 15) & ~7;  // uint16 elements per staging buffer (16-byte multiple)
+  unsigned short* vb = (unsigned short*)smem_raw;
+  for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
+
+  const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
+  float gsum = 0.0f;
+  unsigned orv = 0u;
+
+  if (i0 < i1) {
+    // ---- horizontal taps of this thread's output pixel (registers) ----
+    const int nj = B.j_hi - B.j_lo;
+    const bool hth = tid < nj;
+    const int j = B.j_lo + (hth ? tid : 0);
+    float wx[KX];
+#pragma unroll
+    for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
+    float hbias = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
+    const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
+    int xo = j + B.ox;
+    if (flip) xo = P.cs - 1 - xo;
+    const float post = scale * (1.0f / 128.0f);
+    // where this thread's pixel goes (row term added per output row): intermediate (augmented clips) or dst
+    char* const optr = aug ? (char*)(A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0))
+                           : (char*)A.dst + (dbase + (int64_t)xo * A.sx) * (int64_t)sizeof(DstT);
+
+    // ---- vertical pass state ----
+    const int sh = P.shift - 7;
+    const unsigned rnd = 1u << (sh - 1);
+    unsigned acc0[16], acc1[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = 0u;
+    const int p0 = P.ystart[i0] >> 1;
+    const int plast = (P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1;  // inclusive
+    const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
+    const bool vstore = tid < nchunks;
+    const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
+    const unsigned rs = (unsigned)A.src_row_stride;
+    const unsigned vbytes = (unsigned)vstride * 2u;
+    unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
+    // ---- TMA pipeline: NS stages of one row pair each, filled by bulk copies issued by thread 0 ----
+    const unsigned stage_bytes = 2u * (unsigned)W3;
+    unsigned char* const stage0 = smem_raw + 2u * vbytes;
+    unsigned long long* const bars = (unsigned long long*)(stage0 + (unsigned)NS * stage_bytes);  // full[NS], empty[NS]
+    const unsigned bar_full = (unsigned)__cvta_generic_to_shared(bars), bar_empty = bar_full + 8u * NS;
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage0);
+    if (tid == 0) {
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(bar_full + 8u * s, 1u);
+        mbar_init(bar_empty + 8u * s, (unsigned)(NT / 32));
+      }
+      mbar_fence_init();
+    }
+    __syncthreads();
+    const int n_pairs = plast - p0 + 1;
+    int issued = 0;  // thread 0 only: pairs whose copy has been issued
+    auto issue_pair = [&](int n) {
+      const unsigned s = (unsigned)n % NS;
+      const char* g = frame_base + (size_t)(2 * (p0 + n)) * rs;
+      mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+      if (rs == (unsigned)W3) {
+        bulk_g2s(stage_s + s * stage_bytes, g, stage_bytes, bar_full + 8u * s);
+      } else {
+        bulk_g2s(stage_s + s * stage_bytes, g, (unsigned)W3, bar_full + 8u * s);
+        bulk_g2s(stage_s + s * stage_bytes + (unsigned)W3, g + rs, (unsigned)W3, bar_full + 8u * s);
+      }
+    };
+    if (tid == 0) {
+      for (; issued < min(NS, n_pairs); ++issued) issue_pair(issued);
+    }
+    const unsigned coff = (unsigned)chunk * 16u;
+    uint4 e_nx = __ldg(P.pairs + p0);
+
+#define NEXAR_ACCUM(ACC, WV)                                 \
+  {                                                          \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {          \
+      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], ACC[4 * q + 0]); \
+      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], ACC[4 * q + 1]); \
+      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], ACC[4 * q + 2]); \
+      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], ACC[4 * q + 3]); \
+    }                                                        \
+  }
+#define NEXAR_ACCUM_BEGIN(ACC, WV)                  \
+  {                                                 \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
+      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], rnd);   \
+      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], rnd);   \
+      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], rnd);   \
+      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], rnd);   \
+    }                                               \
+  }
+#define NEXAR_STAGE(ACC)                                                                      \
+  {                                                                                           \
+    unsigned w_[8];                                                                           \
+    _Pragma("unroll") for (int q = 0; q < 8; ++q)                                             \
+        w_[q] = __byte_perm(ACC[2 * q] >> sh, ACC[2 * q + 1] << (16 - sh), 0x7610);           \
+    if (vstore) {                                                                             \
+      uint4* d_ = (uint4*)(smem_raw + bufoff + (unsigned)tid * 32u);                          \
+      d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                                         \
+      d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
+    }                                                                                         \
+  }
+// One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk, NA/NB receive the next pair.
+#define NEXAR_PAIR()                                                                                       \
+  {                                                                                                        \
+    const int n = p - p0;                                                                                  \
+    const unsigned st = (unsigned)n % NS, par = ((unsigned)n / NS) & 1u;                                   \
+    if (tid == 0) { /* producer: refill every stage whose previous round has been released */            \
+      while (issued < n_pairs && issued < n + NS) {                                                        \
+        const unsigned s2 = (unsigned)issued % NS, r2 = (unsigned)issued / NS;                             \
+        if (r2 > 0u && !mbar_test(bar_empty + 8u * s2, (r2 - 1u) & 1u)) break;                             \
+        issue_pair(issued);                                                                                \
+        ++issued;                                                                                          \
+      }                                                                                                    \
+    }                                                                                                      \
+    mbar_wait(bar_full + 8u * st, par);                                                                    \
+    const uint4 CA = *(const uint4*)(stage0 + st * stage_bytes + coff);                                    \
+    const uint4 CB = *(const uint4*)(stage0 + st * stage_bytes + (unsigned)W3 + coff);                     \
+    const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
+    e_nx = __ldg(P.pairs + min(p + 1, plast)); /* control words of the next pair, one iteration ahead */   \
+    orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
+    unsigned lo[4], hi[4];                                                                                 \
+    lo[0] = __byte_perm(CA.x, CB.x, 0x5140); hi[0] = __byte_perm(CA.x, CB.x, 0x7362);                      \
+    lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
+    lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
+    lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
+    __syncwarp();                                                                                          \
+    if ((tid & 31) == 0) mbar_arrive(bar_empty + 8u * st); /* this warp is done with the stage */          \
+    if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
+      if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
+      if (ey) NEXAR_ACCUM(acc1, ey)                                                                      \
+    } else {                                                                                               \
+      if (ex) {                                                                                           \
+        if (ez & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, ex) else NEXAR_ACCUM(acc0, ex)                 \
+      }                                                                                                    \
+      if (ey) {                                                                                           \
+        if (ez & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, ey) else NEXAR_ACCUM(acc1, ey)                 \
+      }                                                                                                    \
+    }                                                                                                      \
+    if (ez & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
+      const int row = (int)((ez >> NEXAR_E_ROWSHIFT) & 0xFFFu);                                                      \
+      const bool s1 = (ez & NEXAR_E_SLOT) != 0u;                                                          \
+      if (row >= i0 && row < i1) {                                                                         \
+        if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
+        __syncthreads();                                                                                   \
+        if (hth) {                                                                                         \
+          const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
+          float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
+          unsigned w0 = src[0], w1 = src[1], w2 = src[2];                                                  \
+          _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
+            unsigned n0 = 0u, n1 = 0u, n2 = 0u;                                                            \
+            if (k + 2 < KX) { n0 = src[3 * (k >> 1) + 3]; n1 = src[3 * (k >> 1) + 4]; n2 = src[3 * (k >> 1) + 5]; } \
+            r = fmaf(wx[k], magic_lo(w0), r);                                                              \
+            g = fmaf(wx[k], magic_hi(w0), g);                                                              \
+            bl = fmaf(wx[k], magic_lo(w1), bl);                                                            \
+            r = fmaf(wx[k + 1], magic_hi(w1), r);                                                          \
+            g = fmaf(wx[k + 1], magic_lo(w2), g);                                                          \
+            bl = fmaf(wx[k + 1], magic_hi(w2), bl);                                                        \
+            w0 = n0; w1 = n1; w2 = n2;                                                                     \
+          }                                                                                                \
+          r = (r - hbias) * post;                                                                          \
+          g = (g - hbias) * post;                                                                          \
+          bl = (bl - hbias) * post;                                                                        \
+          const int y = row + B.oy;                                                                        \
+          if (aug) {                                                                                       \
+            const float bright = cp->brightness;                                                           \
+            r = clamp01(__fmul_rn(bright, r));                                                             \
+            g = clamp01(__fmul_rn(bright, g));                                                             \
+            bl = clamp01(__fmul_rn(bright, bl));                                                           \
+            gsum += gray_of(r, g, bl);                                                                     \
+            ((float4*)optr)[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                              \
+          } else {                                                                                         \
+            DstT* const o = (DstT*)optr + (int64_t)y * A.sy;                                               \
+            if (A.normalize) {                                                                             \
+              r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
+              g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
+              bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
+            }                                                                                              \
+            store_out<DstT>(o, 0, r);                                                                      \
+            store_out<DstT>(o, A.sc, g);                                                                   \
+            store_out<DstT>(o, 2 * A.sc, bl);                                                              \
+          }                                                                                                \
+        }                                                                                                  \
+        bufoff = vbytes - bufoff; /* other staging buffer */                                               \
+      }                                                                                                    \
+      const unsigned wpost = ez & 0xFFFF0000u;                                                             \
+      if (wpost) { /* first tap of the slot's next row shares this pair */                                 \
+        if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                         \
+      }                                                                                                    \
+    }                                                                                                      \
+  }
+
+    for (int p = p0; p <= plast; ++p) NEXAR_PAIR()
+#undef NEXAR_PAIR
+#undef NEXAR_ACCUM
+#undef NEXAR_ACCUM_BEGIN
+#undef NEXAR_STAGE
+  }
+
+  if (!aug) fill_pads<DstT, NT>(P, A, B, dbase, band, nb, i0, i1, tid);
   if (A.pass == 0) {
     const bool big = (orv & 0xFEFEFEFEu) != 0u;
     if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
@@ -1240,14 +1533,34 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
     K.pass = 0;
+    const bool use_tma = g_resize_variant == 3;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
+    const size_t stage_bytes = 2 * (size_t)P.src_w * 3;
+    const int ns = need_threads <= 256 ? NEXAR_STAGES : (stage_bytes > 8192 ? 4 : NEXAR_STAGES);
+    const size_t smem_tma = smem + ns * stage_bytes + 16 * ns;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
 #define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K)
-    if (need_threads <= 256) {
+#define NEXAR_TMA(KXV, NTV, MB, NSV)                                                                              \
+  {                                                                                                               \
+    auto kern = resize_tma_kernel<KXV, NTV, MB, NSV, DstT>;                                                        \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));              \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    kern<<<grid, NTV, smem_tma, st>>>(P, K);                                                                       \
+  }
+    if (use_tma) {
+      if (need_threads <= 256) {
+        if (kx == 10) NEXAR_TMA(10, 256, NEXAR_MINB, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 256, NEXAR_MINB, NEXAR_STAGES) else NEXAR_TMA(20, 256, 2, NEXAR_STAGES)
+      } else if (ns == 4) {
+        if (kx == 10) NEXAR_TMA(10, 384, 2, 4) else if (kx == 14) NEXAR_TMA(14, 384, 2, 4) else NEXAR_TMA(20, 384, 2, 4)
+      } else {
+        if (kx == 10) NEXAR_TMA(10, 384, 2, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 384, 2, NEXAR_STAGES) else NEXAR_TMA(20, 384, 2, NEXAR_STAGES)
+      }
+    } else if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB); else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB); else NEXAR_FAST(20, 256, 2);
     } else {
       if (kx == 10) NEXAR_FAST(10, 384, 2); else if (kx == 14) NEXAR_FAST(14, 384, 2); else NEXAR_FAST(20, 384, 2);
     }
 #undef NEXAR_FAST
+#undef NEXAR_TMA
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
     // fix-up of clips whose maximum was <= 1 (not divided by 255): their values live in [0,1], below the
     // resolution of the 15-bit staging, so the rare second pass uses the fp32 kernel.  Same band count:
