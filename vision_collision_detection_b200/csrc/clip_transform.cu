@@ -382,11 +382,24 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 
 static const int kMaxBands = 16;
 
+// Per-frame constants computed once by K1.5 (frame_stats_kernel) so that K2/K3 start with a few 16-byte loads
+// instead of re-deriving the content box, the colour parameters and the pad colour in every thread.
+struct alignas(16) FrameInfo {
+  float padr, padg, padb, cmean;          // colour of a zero (pad) pixel after the colour chain; contrast_q * gray mean
+  int by0, by1, bx0, bx1;                 // content box on the canvas (x already mirrored for flipped clips)
+  float grid[6];                          // affine grid coefficients
+  unsigned flags;
+  float contrast;
+  float saturation, saturation_q, hue;
+  int reserved;
+};
+static_assert(sizeof(FrameInfo) == 80, "FrameInfo is five 16-byte words");
+
 
 struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
   float* gray_partial;  // [2][n_frames][kMaxBands]
-  float4* pad_colour;   // [n_frames] colour of a zero (pad) pixel after the colour chain (written by K2)
+  FrameInfo* finfo;     // [n_frames] per-frame constants for K2/K3, written by K1.5
   float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
   size_t total;
@@ -402,8 +415,8 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base) {
   off = align_up(off + (size_t)n_clips * sizeof(unsigned), 256);
   w.gray_partial = (float*)(b + off);
   off = align_up(off + 2 * nf * kMaxBands * sizeof(float), 256);
-  w.pad_colour = (float4*)(b + off);
-  off = align_up(off + nf * sizeof(float4), 256);
+  w.finfo = (FrameInfo*)(b + off);
+  off = align_up(off + nf * sizeof(FrameInfo), 256);
   w.inter = (float4*)(b + off);
   off = align_up(off + nf * bh * bw * sizeof(float4), 256);
   w.canvas = (float*)(b + off);
@@ -432,7 +445,7 @@ struct KArgs {
   float nscale[3], nbias[3];  // out = v * nscale + nbias  ((v - mean) / std)
   unsigned* clip_max;
   float* gray_partial;
-  float4* pad_colour;
+  FrameInfo* finfo;
   float4* inter;
   float* canvas;
   int n_frames;
@@ -1266,31 +1279,54 @@ __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, in
   return s / (float)(P.cs * P.cs);
 }
 
-// K2: contrast/saturation/hue in place on the frame's content box (which always fills the
-// [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them).
-// Block (0, frame) also publishes the colour a zero pad pixel takes, for K3.
-constexpr int kColourPerThread = 4;
-__global__ void __launch_bounds__(256) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, int nbands) {
-  __shared__ ColourParams S;
-  const int frame = blockIdx.y;
+// K1.5: one thread per frame.  Reduces the band partial sums to the frame's gray mean (fixed order:
+// deterministic) and evaluates the colour a zero pad pixel takes after the colour chain.
+// stats[frame] = (pad r, pad g, pad b, contrast_q * mean).
+__global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, int nbands) {
+  const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= A.n_frames) return;
   const int clip = frame / A.T;
   const NexarClipParams* cp = A.params + clip;
-  if (!(cp->flags & NEXAR_AUG)) return;
-  if (threadIdx.x == 0) {
-    const int slot = A.clip_max[clip] != 0u ? 0 : 1;
-    S.cmean = __fmul_rn(cp->contrast_q, frame_mean(A, P, frame, slot, nbands));
-    S.contrast = cp->contrast;
-    S.saturation = cp->saturation;
-    S.saturation_q = cp->saturation_q;
-    S.hue = cp->hue;
-    if (blockIdx.x == 0) {
-      float r = 0.0f, g = 0.0f, b = 0.0f;
-      colour_chain(r, g, b, S);
-      A.pad_colour[frame] = make_float4(r, g, b, 0.0f);
-    }
+  FrameInfo fi;
+  fi.flags = cp->flags;
+  fi.reserved = 0;
+  if (!(fi.flags & NEXAR_AUG)) {
+    A.finfo[frame].flags = 0u;
+    return;
   }
-  __syncthreads();
-  const ColourParams c = S;
+  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
+  ColourParams c;
+  c.cmean = __fmul_rn(cp->contrast_q, frame_mean(A, P, frame, slot, nbands));
+  c.contrast = cp->contrast;
+  c.saturation = cp->saturation;
+  c.saturation_q = cp->saturation_q;
+  c.hue = cp->hue;
+  float r = 0.0f, g = 0.0f, b = 0.0f;
+  colour_chain(r, g, b, c);
+  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, fi.flags & NEXAR_FLIP);
+  fi.padr = r; fi.padg = g; fi.padb = b; fi.cmean = c.cmean;
+  fi.by0 = B.by0; fi.by1 = B.by1; fi.bx0 = B.bx0; fi.bx1 = B.bx1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) fi.grid[k] = cp->grid[k];
+  fi.contrast = c.contrast; fi.saturation = c.saturation; fi.saturation_q = c.saturation_q; fi.hue = c.hue;
+  A.finfo[frame] = fi;
+}
+
+// K2: contrast/saturation/hue in place on the frame's content box (which always fills the
+// [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them).
+// The result is stored RELATIVE to the pad colour, so that K3 can treat pad neighbours as zeros.
+constexpr int kColourPerThread = 4;
+__global__ void __launch_bounds__(256) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  const int frame = blockIdx.y;
+  const float4* fi4 = (const float4*)(A.finfo + frame);
+  const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, hue, -
+  if (!(__float_as_uint(q3.z) & NEXAR_AUG)) return;
+  ColourParams c;
+  c.cmean = st.w;
+  c.contrast = q3.w;
+  c.saturation = q4.x;
+  c.saturation_q = q4.y;
+  c.hue = q4.z;
   const int n = A.bh * A.bw;
   float4* base = A.inter + (size_t)frame * n;
   const int i0 = blockIdx.x * (256 * kColourPerThread) + threadIdx.x;
@@ -1302,6 +1338,9 @@ __global__ void __launch_bounds__(256) colour_kernel(const __grid_constant__ Dev
   for (int k = 0; k < kColourPerThread; ++k)
     if (i0 + k * 256 < n) {
       colour_chain(v[k].x, v[k].y, v[k].z, c);
+      v[k].x -= st.x;
+      v[k].y -= st.y;
+      v[k].z -= st.z;
       base[i0 + k * 256] = v[k];
     }
 }
@@ -1348,93 +1387,117 @@ __device__ __forceinline__ void point_effects(float& r, float& g, float& b, cons
   }
 }
 
-// Thread block = 32 x 32 output pixels of one frame, four rows per thread.  A tile whose four
-// corners map (affine maps are linear, so the corners bound the tile) strictly inside the canvas and
-// entirely into the pad band beside the content is filled with the constant pad colour without
-// touching the intermediate.
+// Thread block = 32 x 32 output pixels of one frame, four rows per thread (rows ty, ty+8, ty+16, ty+24).
+// Each of the four 32 x 8 sub-tiles is classified once from its corners (affine maps are linear, so the
+// corners bound the sub-tile): FILL — maps strictly inside the canvas and entirely into the pad band
+// beside the content: constant pad colour, no memory traffic; INTERIOR — every bilinear neighbour is a
+// content pixel: four unconditional loads; otherwise the general path, which clamps the four addresses
+// into the content box and zeroes the weights of neighbours that are pad or outside the canvas (the
+// intermediate is stored relative to the pad colour, so pad neighbours contribute through the mask only).
 constexpr int kGeoRows = 4;
+enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
 template <typename DstT>
 __global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  __shared__ int cls_s[kGeoRows];
   const int frame = blockIdx.z;
+  const float4* fi4 = (const float4*)(A.finfo + frame);
+  const float4 padv = __ldg(fi4), q2 = __ldg(fi4 + 2), q3 = __ldg(fi4 + 3);
+  const int4 bx = __ldg((const int4*)fi4 + 1);
+  const unsigned flags = __float_as_uint(q3.z);
+  if (!(flags & NEXAR_AUG)) return;
   const int clip = frame / A.T;
   const int t = frame - clip * A.T;
-  const NexarClipParams* cp = A.params + clip;
-  const unsigned flags = cp->flags;
-  if (!(flags & NEXAR_AUG)) return;
-  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flags & NEXAR_FLIP);
+  const NexarClipParams* cp = A.params + clip;   // only the rare tail effects read it
+  struct { int by0, by1, bx0, bx1; } B = {bx.x, bx.y, bx.z, bx.w};
   const int cs = P.cs;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + tx, ybase = blockIdx.y * 32 + ty;
-  const float half = (float)cs * 0.5f;
-  const float4 padv = A.pad_colour[frame];
-  const float g0 = cp->grid[0], g1 = cp->grid[1], g2 = cp->grid[2], g3 = cp->grid[3], g4 = cp->grid[4], g5 = cp->grid[5];
-  bool fill = false;
-  if (flags & NEXAR_AFFINE) {
-    float ymin = 1e30f, ymax = -1e30f, xmin = 1e30f, xmax = -1e30f;
+  const float half = (float)cs * 0.5f, fcs = (float)cs;
+  const bool affine = (flags & NEXAR_AFFINE) != 0u;
+  const float g0 = q2.x, g1 = q2.y, g2 = q2.z, g3 = q2.w, g4 = q3.x, g5 = q3.y;
+  if (threadIdx.x < kGeoRows) {
+    int cls = GEO_GENERAL;
+    if (affine) {
+      float ymin = 1e30f, ymax = -1e30f, xmin = 1e30f, xmax = -1e30f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float xb = (float)min((int)blockIdx.x * 32 + (c & 1) * 31, cs - 1) - half + 0.5f;
-      const float yb = (float)min((int)blockIdx.y * 32 + (c >> 1) * 31, cs - 1) - half + 0.5f;
-      const float sx = fmaf(fmaf(yb, g1, xb * g0) + g2 + 1.0f, (float)cs, -1.0f) * 0.5f;
-      const float sy = fmaf(fmaf(yb, g4, xb * g3) + g5 + 1.0f, (float)cs, -1.0f) * 0.5f;
-      xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
-      ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+      for (int c = 0; c < 4; ++c) {
+        const float xb = (float)min((int)blockIdx.x * 32 + (c & 1) * 31, cs - 1) - half + 0.5f;
+        const float yb = (float)min((int)blockIdx.y * 32 + 8 * (int)threadIdx.x + (c >> 1) * 7, cs - 1) - half + 0.5f;
+        const float sx = fmaf(fmaf(yb, g1, xb * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
+        const float sy = fmaf(fmaf(yb, g4, xb * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
+        xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
+        ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+      }
+      // 0.01 px of slack for fp rounding differences between the corner and per-pixel evaluation
+      const bool inside = xmin >= 0.01f && xmax <= fcs - 1.01f && ymin >= 0.01f && ymax <= fcs - 1.01f;
+      const bool above = ymax + 1.01f < (float)B.by0, below = ymin - 0.01f >= (float)B.by1;
+      const bool left = xmax + 1.01f < (float)B.bx0, right = xmin - 0.01f >= (float)B.bx1;
+      const bool interior = xmin >= (float)B.bx0 + 0.01f && xmax <= (float)B.bx1 - 1.01f &&
+                            ymin >= (float)B.by0 + 0.01f && ymax <= (float)B.by1 - 1.01f;
+      cls = (inside && (above || below || left || right)) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
     }
-    // 0.01 px of slack for fp rounding differences between the corner and per-pixel evaluation
-    const bool inside = xmin >= 0.01f && xmax <= (float)(cs - 1) - 0.01f && ymin >= 0.01f && ymax <= (float)(cs - 1) - 0.01f;
-    const bool above = ymax + 1.01f < (float)B.by0, below = ymin - 0.01f >= (float)B.by1;
-    const bool left = xmax + 1.01f < (float)B.bx0, right = xmin - 0.01f >= (float)B.bx1;
-    fill = inside && (above || below || left || right);
+    cls_s[threadIdx.x] = cls;
   }
+  __syncthreads();
   if (x >= cs) return;
-  const float4* fr = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;  // indexed by canvas (y, x)
+  const float4* fr = A.inter + (int64_t)frame * (A.bh * A.bw) - (B.by0 * A.bw + B.bx0);  // indexed by canvas (y, x)
   const float xb = (float)x - half + 0.5f;
-  const int64_t obase = (int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)x * A.sx;
+  DstT* const obase = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)x * A.sx);
   const bool tail_fx = (flags & (NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT)) != 0u;
+  const float ns0 = A.normalize ? A.nscale[0] : 1.0f, ns1 = A.normalize ? A.nscale[1] : 1.0f, ns2 = A.normalize ? A.nscale[2] : 1.0f;
+  const float nb0 = A.normalize ? A.nbias[0] : 0.0f, nb1 = A.normalize ? A.nbias[1] : 0.0f, nb2 = A.normalize ? A.nbias[2] : 0.0f;
 #pragma unroll
   for (int k = 0; k < kGeoRows; ++k) {
     const int y = ybase + 8 * k;
     if (y >= cs) break;
+    const int cls = cls_s[k];
     float r, g, b;
-    if (fill) {
+    if (cls == GEO_FILL) {
       r = padv.x; g = padv.y; b = padv.z;
-    } else if (flags & NEXAR_AFFINE) {
+    } else if (affine) {
       // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
       const float yb = (float)y - half + 0.5f;
       const float gx = fmaf(yb, g1, xb * g0) + g2;
       const float gy = fmaf(yb, g4, xb * g3) + g5;
-      const float ix = fmaf(gx + 1.0f, (float)cs, -1.0f) * 0.5f;
-      const float iy = fmaf(gy + 1.0f, (float)cs, -1.0f) * 0.5f;
+      const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
+      const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
       const float x0f = floorf(ix), y0f = floorf(iy);
       const float wx1 = ix - x0f, wy1 = iy - y0f;
       const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-      // clamp before the int cast so wild matrices cannot overflow
-      const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)cs + 1.0f);
-      const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)cs + 1.0f);
-      const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
-      const bool iny0 = (unsigned)y0 < (unsigned)cs, iny1 = (unsigned)(y0 + 1) < (unsigned)cs;
-      const float w00 = (inx0 && iny0) ? wx0 * wy0 : 0.0f, w01 = (inx1 && iny0) ? wx1 * wy0 : 0.0f;
-      const float w10 = (inx0 && iny1) ? wx0 * wy1 : 0.0f, w11 = (inx1 && iny1) ? wx1 * wy1 : 0.0f;
-      const float m = (w00 + w01) + (w10 + w11);
-      if (y0 + 1 < B.by0 || y0 >= B.by1 || x0 + 1 < B.bx0 || x0 >= B.bx1) {
-        r = padv.x * m; g = padv.y * m; b = padv.z * m;  // every neighbour is a pad pixel (or outside the canvas)
+      if (cls == GEO_INTERIOR) {
+        const float4* row0 = fr + (int64_t)((int)y0f * A.bw + (int)x0f);
+        const float4 v00 = __ldg(row0), v01 = __ldg(row0 + 1), v10 = __ldg(row0 + A.bw), v11 = __ldg(row0 + A.bw + 1);
+        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+        r = padv.x + fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00)));
+        g = padv.y + fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00)));
+        b = padv.z + fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00)));
       } else {
+        // clamp before the int cast so wild matrices cannot overflow
+        const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
+        const int y0 = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
+        const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
+        const bool iny0 = (unsigned)y0 < (unsigned)cs, iny1 = (unsigned)(y0 + 1) < (unsigned)cs;
+        const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
+        const float m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
         const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
         const bool cy0 = y0 >= B.by0 && y0 < B.by1, cy1 = y0 + 1 >= B.by0 && y0 + 1 < B.by1;
-        const float4* row0 = fr + (int64_t)y0 * A.bw + x0;
-        const float4* row1 = row0 + A.bw;
-        const float4 v00 = (cx0 && cy0) ? __ldg(row0) : padv, v01 = (cx1 && cy0) ? __ldg(row0 + 1) : padv;
-        const float4 v10 = (cx0 && cy1) ? __ldg(row1) : padv, v11 = (cx1 && cy1) ? __ldg(row1 + 1) : padv;
-        r = fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00)));
-        g = fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00)));
-        b = fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00)));
+        const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
+        const int xc0 = min(max(x0, B.bx0), B.bx1 - 1), xc1 = min(max(x0 + 1, B.bx0), B.bx1 - 1);
+        const int yc0 = min(max(y0, B.by0), B.by1 - 1), yc1 = min(max(y0 + 1, B.by0), B.by1 - 1);
+        const float4* row0 = fr + (int64_t)(yc0 * A.bw);
+        const float4* row1 = fr + (int64_t)(yc1 * A.bw);
+        const float4 v00 = __ldg(row0 + xc0), v01 = __ldg(row0 + xc1), v10 = __ldg(row1 + xc0), v11 = __ldg(row1 + xc1);
+        const float w00 = bx0w * by0w, w01 = bx1w * by0w, w10 = bx0w * by1w, w11 = bx1w * by1w;
+        r = fmaf(padv.x, m, fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00))));
+        g = fmaf(padv.y, m, fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00))));
+        b = fmaf(padv.z, m, fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00))));
+        r *= m;  // img * mask + (1 - mask) * 0
+        g *= m;
+        b *= m;
       }
-      r *= m;  // img * mask + (1 - mask) * 0
-      g *= m;
-      b *= m;
     } else if (y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1) {
-      const float4 v = __ldg(fr + (int64_t)y * A.bw + x);
-      r = v.x; g = v.y; b = v.z;
+      const float4 v = __ldg(fr + (int64_t)(y * A.bw + x));
+      r = padv.x + v.x; g = padv.y + v.y; b = padv.z + v.z;
     } else {
       r = padv.x; g = padv.y; b = padv.z;
     }
@@ -1456,15 +1519,10 @@ __global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ D
       }
       point_effects(r, g, b, cp, flags, y, x);
     }
-    const int64_t o = obase + (int64_t)y * A.sy;
-    if (A.normalize) {
-      r = fmaf(r, A.nscale[0], A.nbias[0]);
-      g = fmaf(g, A.nscale[1], A.nbias[1]);
-      b = fmaf(b, A.nscale[2], A.nbias[2]);
-    }
-    store_out<DstT>(A.dst, o, r);
-    store_out<DstT>(A.dst, o + A.sc, g);
-    store_out<DstT>(A.dst, o + 2 * A.sc, b);
+    DstT* const o = obase + (int64_t)y * A.sy;
+    store_out<DstT>(o, 0, fmaf(r, ns0, nb0));
+    store_out<DstT>(o, A.sc, fmaf(g, ns1, nb1));
+    store_out<DstT>(o, 2 * A.sc, fmaf(b, ns2, nb2));
   }
 }
 
@@ -1595,9 +1653,10 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   }
   if (aug_mode) {
     const int cs = P.cs;
-    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K, nbands);
+    frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
+    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
     geometry_kernel<DstT><<<dim3((cs + 31) / 32, (cs + 31) / 32, nf), 256, 0, st>>>(P, K);
-    g_launches += 2;
+    g_launches += 3;
     if (blur_mode) {
       blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
       ++g_launches;
@@ -1643,7 +1702,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   }
   K.clip_max = w.clip_max;
   K.gray_partial = w.gray_partial;
-  K.pad_colour = w.pad_colour;
+  K.finfo = w.finfo;
   K.inter = w.inter;
   K.canvas = w.canvas;
   K.n_frames = a->n_clips * a->frames_per_clip;

@@ -126,49 +126,55 @@ def gaussian_taps(sigma: float) -> np.ndarray:
     return (pdf / pdf.sum(dtype=F32)).astype(F32)
 
 
+_F = {name: (_lib.CLIP_PARAMS_DTYPE.fields[name][1] // 4) for name in _lib.CLIP_PARAMS_DTYPE.names}   # word offset of each field
+_WORDS = _lib.CLIP_PARAMS_DTYPE.itemsize // 4
+
+
 def pack_clip_params(records: Sequence[Dict[str, Any]], canvas: int,
                      aug_cfg: Optional[VideoAugmentation] = None) -> Tuple[np.ndarray, int]:
     """records[i] = {'flip': bool, 'aug': dict|None, 'crop': (dy, dx)|None} ->
     (structured array of NexarClipParams, OR of all flags).  Raises the errors
-    torchvision would raise for out-of-range factors."""
-    out = np.zeros(len(records), _lib.CLIP_PARAMS_DTYPE)
+    torchvision would raise for out-of-range factors.  Scalars are gathered into
+    per-field columns and written with a few vectorised assignments (this runs once
+    per batch on the host, in front of every kernel launch)."""
+    n = len(records)
+    words = np.zeros((n, _WORDS), np.uint32)
+    fview = words.view(F32)
+    iview = words.view(np.int32)
+    flags_col = [0] * n
+    # neutral values so that an un-augmented clip is well defined: brightness, contrast, saturation = 1
+    colour = [[1.0, 1.0, 0.0, 1.0, 0.0, 0.0] for _ in range(n)]   # brightness, contrast, contrast_q, saturation, saturation_q, hue
+    grids: List[Tuple[int, List[float]]] = []
+    half = float(F32(0.5 * canvas))
     any_flags = 0
     for i, rec in enumerate(records):
-        r = out[i]
         flags = _lib.FLIP if rec.get("flip") else 0
         crop = rec.get("crop")
         if crop is not None:
-            r["crop_dy"], r["crop_dx"] = int(crop[0]), int(crop[1])
-        # neutral values so that an un-augmented clip is well defined
-        r["brightness"] = r["contrast"] = r["saturation"] = 1.0
+            iview[i, _F["crop_dy"]] = int(crop[0])
+            iview[i, _F["crop_dx"]] = int(crop[1])
         p = rec.get("aug")
         if p is not None and not p.get("skip_augmentation", False):
             if aug_cfg is None:
                 raise ValueError("augmentation parameters given without the VideoAugmentation config")
             flags |= _lib.AUG
-            for name in ("brightness", "contrast", "saturation"):
-                if p[name] < 0:
-                    raise ValueError(f"{name}_factor ({p[name]}) is not non-negative.")  # tv:_functional_tensor.py:172,182,225
-            if not (-0.5 <= p["hue"] <= 0.5):
-                raise ValueError(f"hue_factor ({p['hue']}) is not in [-0.5, 0.5].")       # tv:_functional_tensor.py:199
-            r["brightness"] = F32(p["brightness"])
-            r["contrast"], r["contrast_q"] = F32(p["contrast"]), F32(1.0 - p["contrast"])
-            r["saturation"], r["saturation_q"] = F32(p["saturation"]), F32(1.0 - p["saturation"])
-            r["hue"] = F32(p["hue"])
+            br, co, sa, hu = p["brightness"], p["contrast"], p["saturation"], p["hue"]
+            if br < 0 or co < 0 or sa < 0:      # tv:_functional_tensor.py:172,182,225
+                name, val = next((k, v) for k, v in (("brightness", br), ("contrast", co), ("saturation", sa)) if v < 0)
+                raise ValueError(f"{name}_factor ({val}) is not non-negative.")
+            if not (-0.5 <= hu <= 0.5):          # tv:_functional_tensor.py:199
+                raise ValueError(f"hue_factor ({hu}) is not in [-0.5, 0.5].")
+            colour[i] = [br, co, 1.0 - co, sa, 1.0 - sa, hu]
             if p["apply_affine"]:
                 flags |= _lib.AFFINE
-                m = inverse_affine_matrix(p["rotation"], [p["translate_x"], p["translate_y"]], p["scale"],
-                                          [p["shear"], 0.0])
-                theta = np.asarray(m, F32).reshape(2, 3)
-                half = F32(0.5 * canvas)
-                r["grid"][0:3] = theta[0] / half        # tv _gen_affine_grid: theta^T / [0.5w, 0.5h]
-                r["grid"][3:6] = theta[1] / half
+                grids.append((i, inverse_affine_matrix(p["rotation"], [p["translate_x"], p["translate_y"]],
+                                                       p["scale"], [p["shear"], 0.0])))
             if p["apply_grayscale"]:
                 flags |= _lib.GRAYSCALE
             if p["apply_noise"]:
                 flags |= _lib.NOISE
-                r["noise_level"] = F32(aug_cfg.noise_level)
-                r["noise_seed"] = rec.get("noise_seed", (0x1234567, 0x89ABCDE))
+                fview[i, _F["noise_level"]] = aug_cfg.noise_level
+                words[i, _F["noise_seed"]:_F["noise_seed"] + 2] = rec.get("noise_seed", (0x1234567, 0x89ABCDE))
             if p["apply_blur"]:
                 taps = gaussian_taps(aug_cfg.blur_sigma)
                 if len(taps) > _lib.MAX_BLUR_TAPS:
@@ -177,14 +183,14 @@ def pack_clip_params(records: Sequence[Dict[str, Any]], canvas: int,
                     raise ValueError("blur kernel larger than the frame (reflect padding would fail)")
                 if len(taps) > 1:
                     flags |= _lib.BLUR
-                    r["blur_ksize"] = len(taps)
-                    r["blur_taps"][:len(taps)] = taps
+                    iview[i, _F["blur_ksize"]] = len(taps)
+                    fview[i, _F["blur_taps"]:_F["blur_taps"] + len(taps)] = taps
             if p["apply_posterization"]:
                 flags |= _lib.POSTERIZE
-                r["posterize_bits"] = int(p["posterization_bits"])
+                iview[i, _F["posterize_bits"]] = int(p["posterization_bits"])
             if p["apply_solarization"]:
                 flags |= _lib.SOLARIZE
-                r["solarize_threshold"] = F32(aug_cfg.solarization_threshold)
+                fview[i, _F["solarize_threshold"]] = aug_cfg.solarization_threshold
             if p["apply_color_inversion"]:
                 flags |= _lib.INVERT
             if p["apply_cutout"] and p.get("cutout_boxes"):
@@ -192,9 +198,14 @@ def pack_clip_params(records: Sequence[Dict[str, Any]], canvas: int,
                 if len(boxes) > _lib.MAX_CUTOUT:
                     raise ValueError(f"{len(boxes)} cutout boxes exceed NEXAR_MAX_CUTOUT")
                 flags |= _lib.CUTOUT
-                r["n_cutout"] = len(boxes)
-                for k, bx in enumerate(boxes):
-                    r["cutout"][k] = bx
-        r["flags"] = flags
+                iview[i, _F["n_cutout"]] = len(boxes)
+                iview[i, _F["cutout"]:_F["cutout"] + 4 * len(boxes)] = np.asarray(boxes, np.int32).reshape(-1)
+        flags_col[i] = flags
         any_flags |= flags
-    return out, any_flags
+    words[:, _F["flags"]] = flags_col
+    fview[:, _F["brightness"]:_F["brightness"] + 6] = np.asarray(colour, np.float64).astype(F32)   # float32(python double)
+    if grids:
+        idx = [g[0] for g in grids]
+        theta = np.asarray([g[1] for g in grids], np.float64).astype(F32)     # torch.tensor(matrix, dtype=float32)
+        fview[idx, _F["grid"]:_F["grid"] + 6] = theta / F32(half)             # tv _gen_affine_grid: theta^T / [0.5w, 0.5h]
+    return words.view(_lib.CLIP_PARAMS_DTYPE).reshape(n), any_flags
