@@ -516,39 +516,52 @@ __device__ __forceinline__ Box clip_box(const DevPlan& P, int crop_dy, int crop_
 
 
 // Constant fill of the canvas rows/columns outside a band's content box (the normalised value of a
-// zero pixel).  Whole pad rows of a planar layout go out as 16-byte stores.
+// zero pixel).  Runs of whole pad rows of a planar, row-contiguous layout go out as flat 16-byte stores.
 template <typename DstT, int NT>
 __device__ __forceinline__ void fill_pads(const DevPlan& P, const KArgs& A, const Box& B, int64_t dbase, int band, int nb,
                                           int i0, int i1, int tid) {
-  const int Y0 = band == 0 ? 0 : i0 + B.oy;
-  const int Y1 = band == nb - 1 ? P.cs : i1 + B.oy;
-  const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;
+  const int cy0 = i0 + B.oy, cy1 = i1 + B.oy;            // content rows of this band
+  const int Y0 = band == 0 ? 0 : cy0;
+  const int Y1 = band == nb - 1 ? P.cs : cy1;
   float nbi[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
   constexpr int EPV = 16 / (int)sizeof(DstT);  // elements per 16-byte store
-  const bool vec_ok = A.sx == 1 && (P.cs % EPV) == 0 && (A.sy % EPV) == 0 && (A.sc % EPV) == 0 && (A.st % EPV) == 0 &&
+  const bool vec_ok = A.sx == 1 && A.sy == P.cs && (P.cs % EPV) == 0 && (A.sc % EPV) == 0 && (A.st % EPV) == 0 &&
                       (A.sb % EPV) == 0 && (((uintptr_t)A.dst) & 15) == 0;
-  for (int y = Y0; y < Y1; ++y) {
-    const bool content_row = (y >= cy0 && y < cy1) && B.bx1 > B.bx0;
-    if (!content_row && vec_ok) {
-      const int nvec = P.cs / EPV;
-      for (int v = tid; v < 3 * nvec; v += NT) {
-        const int c = v / nvec, xv = v - c * nvec;
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {                 // pad rows above / below the band's content
+    const int ya = part == 0 ? Y0 : cy1, yb = part == 0 ? cy0 : Y1;
+    if (yb <= ya) continue;
+    if (vec_ok) {
+      const int nvec = (yb - ya) * (P.cs / EPV);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
         DstT tmp[EPV];
 #pragma unroll
         for (int k = 0; k < EPV; ++k) store_out<DstT>(tmp, k, nbi[c]);
-        DstT* d = (DstT*)A.dst + dbase + (int64_t)y * A.sy + (int64_t)c * A.sc + (int64_t)xv * EPV;
-        *(uint4*)d = *(const uint4*)tmp;
+        const uint4 val = *(const uint4*)tmp;
+        uint4* d = (uint4*)((DstT*)A.dst + dbase + (int64_t)ya * A.sy + (int64_t)c * A.sc);
+        for (int v = tid; v < nvec; v += NT) d[v] = val;
       }
-      continue;
-    }
-    for (int x = tid; x < P.cs; x += NT) {
-      if (content_row && x >= B.bx0 && x < B.bx1) continue;
-      const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+    } else {
+      for (int y = ya; y < yb; ++y)
+        for (int x = tid; x < P.cs; x += NT) {
+          const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+          for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+        }
     }
+  }
+  if (B.bx0 > 0 || B.bx1 < P.cs) {                       // pad columns beside the content (portrait sources)
+    const int npad = B.bx0 + (P.cs - B.bx1);
+    for (int y = cy0; y < cy1; ++y)
+      for (int k = tid; k < npad; k += NT) {
+        const int x = k < B.bx0 ? k : B.bx1 + (k - B.bx0);
+        const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_out<DstT>(A.dst, o + c * A.sc, nbi[c]);
+      }
   }
 }
 
