@@ -30,6 +30,9 @@ WORKLOADS = {
     "cfg2": (32, 16, 720, 1280, 224),
     "cfg3": (32, 32, 720, 1280, 320),
     "tiny": (4, 4, 180, 320, 112),
+    # BASELINE configs[3]: one 40 s x 30 fps 720p video, val chain, every frame transformed once,
+    # 16-frame windows at stride 8 as strided views (149 windows); "clips" = windows
+    "cfg4": (1, 1200, 720, 1280, 224),
 }
 # the live train call site nexar_videos.py:2003-2010
 KW = {
@@ -165,6 +168,47 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg4(args, rank, world, dev, out_dtype):
+    """Inference windowing (BASELINE configs[3]): per-frame-once val transform of a 1200-frame 720p video."""
+    import torch.distributed as dist
+    from vision_collision_detection_b200.inference import SlidingWindowTransform, sliding_window_starts
+    from vision_collision_detection_b200.synth import make_clip_torch
+    _, n, h, w, cs = WORKLOADS["cfg4"]
+    video = torch.cat([make_clip_torch(100, h, w, seed=rank * 100 + i, kind="dashcam", device=dev) for i in range(n // 100)])
+    sw = SlidingWindowTransform(window=16, stride=8, out_dtype=out_dtype)
+    for _ in range(max(3, args.warmup)):
+        view = sw.windows(video)
+    torch.cuda.synchronize()
+    steps = min(args.steps, 50)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        view = sw.windows(video)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        peaks, kind = measured_peaks()
+        k = len(sliding_window_starts(n, 16, 8))
+        bytes_alg = n * h * w * 3 + n * 3 * cs * cs * (2 if out_dtype == torch.bfloat16 else 4)
+        ach = bytes_alg / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": world * k / (ms * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4: {n} frames {h}x{w} u8 (40 s x 30 fps) -> val chain {cs}x{cs} {args.out_dtype}, every frame once, "
+                                   f"{k} windows of 16 at stride 8 as strided views", "windows_shape": list(view.shape)},
+            "ms_per_video": ms,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                         "peak_kind": kind, "algorithmic_bytes_per_launch": bytes_alg, "traffic": None},
+            "gpu_launches": 2 * steps}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +247,8 @@ def main():
 
     b, t, h, w, cs = WORKLOADS[args.workload]
     out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
+    if args.workload == "cfg4":
+        return run_cfg4(args, rank, world, dev, out_dtype)
     tf = create_video_transforms(**KW[args.mode], crop_size=cs, out_dtype=out_dtype)
     eng = get_engine(dev)
     if os.environ.get("NEXAR_FAST_BANDS"):

@@ -135,6 +135,8 @@ int nexar_plan_geometry(const NexarPlan* plan, NexarGeometry* out);
 /* Bytes of scratch nexar_clip_transform needs for this batch shape (covers the
  * worst case: every clip augmented and blurred). */
 size_t nexar_workspace_bytes(const NexarPlan* plan, int32_t n_clips, int32_t frames_per_clip);
+/* Exact requirement for a batch whose NexarTransformArgs.any_flags is known (no augmentation: a few KB). */
+size_t nexar_workspace_bytes_for(const NexarPlan* plan, int32_t n_clips, int32_t frames_per_clip, uint32_t any_flags);
 
 /* The hot path.  Enqueues the kernels on args->stream and returns. */
 int nexar_clip_transform(const NexarPlan* plan, const NexarTransformArgs* args);

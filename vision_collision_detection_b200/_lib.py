@@ -111,6 +111,8 @@ def lib():
     L.nexar_plan_geometry.argtypes = [C.c_void_p, C.POINTER(Geometry)]
     L.nexar_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.nexar_workspace_bytes.restype = C.c_size_t
+    L.nexar_workspace_bytes_for.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint32]
+    L.nexar_workspace_bytes_for.restype = C.c_size_t
     L.nexar_clip_transform.argtypes = [C.c_void_p, C.POINTER(TransformArgs)]
     L.nexar_last_launch_count.restype = C.c_int
     L.nexar_set_resize_kernel.argtypes = [C.c_int32]

@@ -405,7 +405,7 @@ struct Workspace {
   size_t total;
 };
 
-static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base) {
+static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base, unsigned any_flags) {
   Workspace w;
   const size_t nf = (size_t)n_clips * T;
   const int bh = imin(p->g.resize_h, p->g.canvas), bw = imin(p->g.resize_w, p->g.canvas);
@@ -417,17 +417,21 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base) {
   off = align_up(off + 2 * nf * kMaxBands * sizeof(float), 256);
   w.finfo = (FrameInfo*)(b + off);
   off = align_up(off + nf * sizeof(FrameInfo), 256);
-  w.inter = (float4*)(b + off);
-  off = align_up(off + nf * bh * bw * sizeof(float4), 256);
-  w.canvas = (float*)(b + off);
-  off = align_up(off + nf * 3 * (size_t)p->g.canvas * p->g.canvas * sizeof(float), 256);
+  w.inter = (float4*)(b + off);  // only augmented clips use it
+  if (any_flags & NEXAR_AUG) off = align_up(off + nf * bh * bw * sizeof(float4), 256);
+  w.canvas = (float*)(b + off);  // only the blur path uses it
+  if (any_flags & NEXAR_BLUR) off = align_up(off + nf * 3 * (size_t)p->g.canvas * p->g.canvas * sizeof(float), 256);
   w.total = off;
   return w;
 }
 
 extern "C" size_t nexar_workspace_bytes(const NexarPlan* p, int32_t n_clips, int32_t T) {
   if (!p || n_clips <= 0 || T <= 0) return 0;
-  return carve(p, n_clips, T, nullptr).total;
+  return carve(p, n_clips, T, nullptr, ~0u).total;
+}
+extern "C" size_t nexar_workspace_bytes_for(const NexarPlan* p, int32_t n_clips, int32_t T, uint32_t any_flags) {
+  if (!p || n_clips <= 0 || T <= 0) return 0;
+  return carve(p, n_clips, T, nullptr, any_flags).total;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1686,7 +1690,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   if (a->n_clips <= 0 || a->frames_per_clip <= 0) return fail(NEXAR_ERR_INVALID, "clip_transform: empty batch");
   if (!a->src || !a->frame_offsets || !a->params || !a->dst) return fail(NEXAR_ERR_INVALID, "clip_transform: null buffer");
   if (a->dst_dtype != NEXAR_DST_F32 && a->dst_dtype != NEXAR_DST_BF16) return fail(NEXAR_ERR_INVALID, "clip_transform: bad dst_dtype");
-  const size_t need = nexar_workspace_bytes(p, a->n_clips, a->frames_per_clip);
+  const size_t need = nexar_workspace_bytes_for(p, a->n_clips, a->frames_per_clip, a->any_flags);
   if (!a->workspace || a->workspace_bytes < need) return fail(NEXAR_ERR_WORKSPACE, "clip_transform: workspace too small");
   for (int c = 0; c < 3; ++c)
     if (a->normalize && !(a->std[c] != 0.0f)) return fail(NEXAR_ERR_INVALID, "clip_transform: std must be non-zero");
@@ -1694,7 +1698,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   if (a->src_row_stride < (int64_t)(p->g.src_w * 3 * esz)) return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
 
   if ((int64_t)a->n_clips * a->frames_per_clip > 65535) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: more than 65535 frames per call");
-  Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace);
+  Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace, a->any_flags);
   KArgs K;
   K.src = a->src;
   K.frame_offsets = a->frame_offsets;

@@ -45,8 +45,8 @@ class Plan:
         _lib.check(_lib.lib().nexar_plan_create(C.byref(geom), src_dtype, C.byref(h)))
         self.handle = h
 
-    def workspace_bytes(self, n_clips: int, t: int) -> int:
-        return int(_lib.lib().nexar_workspace_bytes(self.handle, n_clips, t))
+    def workspace_bytes(self, n_clips: int, t: int, any_flags: int = 0xFFFFFFFF) -> int:
+        return int(_lib.lib().nexar_workspace_bytes_for(self.handle, n_clips, t, any_flags & 0xFFFFFFFF))
 
     def __del__(self):
         try:
@@ -150,7 +150,7 @@ class ClipTransformEngine:
             a.dst_stride[i] = int(dst_stride[i])
         for i in range(3):
             a.mean[i], a.std[i] = float(mean[i]), float(std[i])
-        ws = self._get_workspace(plan.workspace_bytes(n_clips, frames_per_clip))
+        ws = self._get_workspace(plan.workspace_bytes(n_clips, frames_per_clip, any_flags))
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
