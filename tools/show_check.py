@@ -16,5 +16,5 @@ try:
         key=(r[ci['ID']], r[ci['Kernel Name']][:40])
         cur.setdefault(key,{})[r[ci['Metric Name']]]=r[ci['Metric Value']]
     for k,v in cur.items():
-        print(k[0], k[1], 'us', float(v['gpu__time_duration.sum'])/1e3, 'rdMB', round(float(v['dram__bytes_read.sum'])/1e6), 'wrMB', round(float(v['dram__bytes_write.sum'])/1e6))
+        print(k[0], k[1], 'us', float(v['gpu__time_duration.sum'])/1e3, 'rdMB', round(float(v['dram__bytes_read.sum'])/1e6), 'wrMB', round(float(v['dram__bytes_write.sum'])/1e6), 'Minst', round(float(v.get('smsp__inst_executed.sum',0))/1e6,1), 'ipc', v.get('sm__inst_issued.avg.per_cycle_active'))
 except Exception as e: print('launch list ERR', e)

@@ -103,7 +103,7 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
   if (std::ldexp((double)wmax, shift) > 65535.0) return false;
   const int n_pairs = (g.src_h + 1) / 2;
   if (n_pairs > kMaxPairs) return false;
-  p->pairs.assign(n_pairs, make_uint4(0, 0, 0, 0));
+  p->pairs.assign(n_pairs + 1, make_uint4(0, 0, 0, 0));  // + one spare entry: the kernel reads one pair ahead
   for (int i = 0; i < g.resize_h; ++i) {
     const int ys = p->ystart[i], yc = p->ycount[i];
     if (yc <= 0) return false;
@@ -145,7 +145,7 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
     if (i >= 4096) return false;
     em |= 1u | ((unsigned)slot << 1) | ((unsigned)i << 4);
   }
-  for (uint4& e : p->pairs) {  // final packing: z = post tap << 16 | out_row << 4 | flags, w unused
+  for (uint4& e : p->pairs) {  // final packing (the spare entry stays zero): z = post tap << 16 | out_row << 4 | flags, w unused
     if (e.w && !(e.z & 1u)) return false;
     e.z = (e.z & 0xFFFFu) | e.w;
     e.w = 0u;
@@ -352,7 +352,7 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   d.ywt = df;
   d.xwt = df + p->ywt.size();
   d.pairs = p->fast_ok ? (const uint4*)p->dev_tables : nullptr;
-  d.n_pairs = (int)p->pairs.size();
+  d.n_pairs = (int)p->pairs.size() - (p->fast_ok ? 1 : 0);
   d.shift = shift;
   d.xstart_al = p->fast_ok ? di + 2 * g->resize_h + 2 * g->resize_w : nullptr;
   d.xwt_al = p->fast_ok ? df + p->ywt.size() + p->xwt.size() : nullptr;
@@ -793,12 +793,22 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const int nj = B.j_hi - B.j_lo;
     const bool hth = tid < nj;
     const int j = B.j_lo + (hth ? tid : 0);
-    float wx[KX];
+    // The taps (and, in the last slot, 2^15 * sum(taps)) live in shared memory, NG float4 groups per thread laid
+    // out group-major so that a warp's LDS.128 is conflict-free; this keeps 14+ registers free for the vertical pass.
+    constexpr int NG = (KX + 1 + 3) / 4;
+    float4* const wsm = (float4*)(smem_raw + 2u * (unsigned)vstride * 2u);
+    {
+      float wtmp[4 * NG];
+      float hb = 0.0f;
 #pragma unroll
-    for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
-    float hbias = 0.0f;
+      for (int k = 0; k < 4 * NG; ++k) {
+        wtmp[k] = (k < KX && hth) ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
+        hb = fmaf(wtmp[k], 32768.0f, hb);
+      }
+      wtmp[4 * NG - 1] = hb;
 #pragma unroll
-    for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
+      for (int g = 0; g < NG; ++g) wsm[g * NT + tid] = make_float4(wtmp[4 * g], wtmp[4 * g + 1], wtmp[4 * g + 2], wtmp[4 * g + 3]);
+    }
     const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
@@ -819,14 +829,13 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const bool vstore = tid < nchunks;
     const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
     const unsigned rs = (unsigned)A.src_row_stride;  // a frame is < 4 GB: 32-bit offsets from the frame base
-    const unsigned step = 2u * rs;
-    const unsigned off_last = (unsigned)(2 * plast) * rs + (unsigned)chunk * 16u;
-    unsigned off = (unsigned)(2 * p0) * rs + (unsigned)chunk * 16u;
+    const unsigned coff = (unsigned)chunk * 16u;
     const unsigned vbytes = (unsigned)vstride * 2u;
     unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
 
-    uint4 a0 = ld_stream(frame_base, off), b0 = ld_stream(frame_base, off + rs);
+    uint4 a0 = ld_stream(frame_base + (size_t)(2 * p0) * rs, coff), b0 = ld_stream(frame_base + (size_t)(2 * p0 + 1) * rs, coff);
     uint4 e_nx = __ldg(P.pairs + p0);
+    const uint4* tp = P.pairs + p0 + 1;
     uint4 a1, b1;
     if (tid < 32) {
       const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
@@ -866,16 +875,14 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
 // One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk, NA/NB receive the next pair.
 #define NEXAR_PAIR(CA, CB, NA, NB)                                                                         \
   {                                                                                                        \
-    off = min(off + step, off_last); /* the tail re-reads the last pair */                                 \
-    NA = ld_stream(frame_base, off);                                                                       \
-    NB = ld_stream(frame_base, off + rs);                                                                  \
-    if (NEXAR_L1PF > 0) {                                                                                  \
-      const unsigned offp = min(off + (unsigned)NEXAR_L1PF * step, off_last);                              \
-      l1_prefetch(frame_base, offp);                                                                       \
-      l1_prefetch(frame_base, offp + rs);                                                                  \
+    { /* next pair; the row offset is computed on the uniform datapath, the tail re-reads the last pair */ \
+      const char* nrow = frame_base + (size_t)(2 * min(p + 1, plast)) * rs;                                \
+      NA = ld_stream(nrow, coff);                                                                          \
+      NB = ld_stream(nrow + rs, coff);                                                                     \
     }                                                                                                      \
     const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
-    e_nx = __ldg(P.pairs + min(p + 1, plast)); /* control words of the next pair, one iteration ahead */   \
+    e_nx = __ldg(tp); /* control words of the next pair, one iteration ahead (table has a spare entry) */  \
+    ++tp;                                                                                                  \
     orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
     unsigned lo[4], hi[4];                                                                                 \
     lo[0] = __byte_perm(CA.x, CB.x, 0x5140); hi[0] = __byte_perm(CA.x, CB.x, 0x7362);                      \
@@ -903,17 +910,21 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
           const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
           float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
           unsigned w0 = src[0], w1 = src[1], w2 = src[2];                                                  \
+          float4 wq = wsm[tid];                                                                            \
           _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
             unsigned n0 = 0u, n1 = 0u, n2 = 0u;                                                            \
             if (k + 2 < KX) { n0 = src[3 * (k >> 1) + 3]; n1 = src[3 * (k >> 1) + 4]; n2 = src[3 * (k >> 1) + 5]; } \
-            r = fmaf(wx[k], magic_lo(w0), r);                                                              \
-            g = fmaf(wx[k], magic_hi(w0), g);                                                              \
-            bl = fmaf(wx[k], magic_lo(w1), bl);                                                            \
-            r = fmaf(wx[k + 1], magic_hi(w1), r);                                                          \
-            g = fmaf(wx[k + 1], magic_lo(w2), g);                                                          \
-            bl = fmaf(wx[k + 1], magic_hi(w2), bl);                                                        \
+            const float wa = (k & 2) ? wq.z : wq.x, wb = (k & 2) ? wq.w : wq.y;                            \
+            r = fmaf(wa, magic_lo(w0), r);                                                                 \
+            g = fmaf(wa, magic_hi(w0), g);                                                                 \
+            bl = fmaf(wa, magic_lo(w1), bl);                                                               \
+            r = fmaf(wb, magic_hi(w1), r);                                                                 \
+            g = fmaf(wb, magic_lo(w2), g);                                                                 \
+            bl = fmaf(wb, magic_hi(w2), bl);                                                               \
             w0 = n0; w1 = n1; w2 = n2;                                                                     \
+            if ((k & 2) && (k + 2) / 4 < NG) wq = wsm[((k + 2) / 4) * NT + tid];                           \
           }                                                                                                \
+          const float hbias = (KX % 4 == 0) ? wsm[(NG - 1) * NT + tid].w : wq.w;                           \
           r = (r - hbias) * post;                                                                          \
           g = (g - hbias) * post;                                                                          \
           bl = (bl - hbias) * post;                                                                        \
@@ -1608,12 +1619,21 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
     K.pass = 0;
-    const bool use_tma = g_resize_variant == 3;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
+    const bool use_tma = g_resize_variant == 3;
+    const int ng = (kx + 1 + 3) / 4;
+    const int nt_fast = need_threads <= 256 ? 256 : 384;
+    const size_t smem_fast = smem + (size_t)ng * nt_fast * 16;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
     const size_t stage_bytes = 2 * (size_t)P.src_w * 3;
     const int ns = need_threads <= 256 ? NEXAR_STAGES : (stage_bytes > 8192 ? 4 : NEXAR_STAGES);
     const size_t smem_tma = smem + ns * stage_bytes + 16 * ns;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
-#define NEXAR_FAST(KXV, NTV, MB) resize_fast_kernel<KXV, NTV, MB, DstT><<<grid, NTV, smem, st>>>(P, K)
+#define NEXAR_FAST(KXV, NTV, MB)                                                                                 \
+  {                                                                                                               \
+    auto kern = resize_fast_kernel<KXV, NTV, MB, DstT>;                                                            \
+    if (smem_fast > 48 * 1024)                                                                                    \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));           \
+    kern<<<grid, NTV, smem_fast, st>>>(P, K);                                                                      \
+  }
 #define NEXAR_TMA(KXV, NTV, MB, NSV)                                                                              \
   {                                                                                                               \
     auto kern = resize_tma_kernel<KXV, NTV, MB, NSV, DstT>;                                                        \
@@ -1630,9 +1650,9 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
         if (kx == 10) NEXAR_TMA(10, 384, 2, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 384, 2, NEXAR_STAGES) else NEXAR_TMA(20, 384, 2, NEXAR_STAGES)
       }
     } else if (need_threads <= 256) {
-      if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB); else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB); else NEXAR_FAST(20, 256, 2);
+      if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB) else NEXAR_FAST(20, 256, 2)
     } else {
-      if (kx == 10) NEXAR_FAST(10, 384, 2); else if (kx == 14) NEXAR_FAST(14, 384, 2); else NEXAR_FAST(20, 384, 2);
+      if (kx == 10) NEXAR_FAST(10, 384, 2) else if (kx == 14) NEXAR_FAST(14, 384, 2) else NEXAR_FAST(20, 384, 2)
     }
 #undef NEXAR_FAST
 #undef NEXAR_TMA
