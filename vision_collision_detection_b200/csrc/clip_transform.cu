@@ -743,7 +743,7 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 #define NEXAR_STAGES 6  // row pairs in flight per CTA in the TMA ring
 #endif
 #ifndef NEXAR_LOOKAHEAD
-#define NEXAR_LOOKAHEAD 12
+#define NEXAR_LOOKAHEAD 4
 #endif
 
 // table entry .w bits
