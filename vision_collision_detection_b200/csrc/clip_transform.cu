@@ -834,9 +834,14 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
 
     uint4 a0 = ld_stream(frame_base + (size_t)(2 * p0) * rs, coff), b0 = ld_stream(frame_base + (size_t)(2 * p0 + 1) * rs, coff);
+    uint4 a1, b1;
+    {
+      const char* nrow = frame_base + (size_t)(2 * min(p0 + 1, plast)) * rs;
+      a1 = ld_stream(nrow, coff);
+      b1 = ld_stream(nrow + rs, coff);
+    }
     uint4 e_nx = __ldg(P.pairs + p0);
     const uint4* tp = P.pairs + p0 + 1;
-    uint4 a1, b1;
     if (tid < 32) {
       const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
       if (tid == 0 && q1 >= q0)
@@ -872,14 +877,11 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
     }                                                                                         \
   }
-// One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk, NA/NB receive the next pair.
-#define NEXAR_PAIR(CA, CB, NA, NB)                                                                         \
+// One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk.  As soon as their bytes have been
+// interleaved into lo/hi the same registers are refilled with pair p+2 (two register sets ping-pong, so
+// every load has almost two iterations to land).
+#define NEXAR_PAIR(CA, CB)                                                                                 \
   {                                                                                                        \
-    { /* next pair; the row offset is computed on the uniform datapath, the tail re-reads the last pair */ \
-      const char* nrow = frame_base + (size_t)(2 * min(p + 1, plast)) * rs;                                \
-      NA = ld_stream(nrow, coff);                                                                          \
-      NB = ld_stream(nrow + rs, coff);                                                                     \
-    }                                                                                                      \
     const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
     e_nx = __ldg(tp); /* control words of the next pair, one iteration ahead (table has a spare entry) */  \
     ++tp;                                                                                                  \
@@ -889,6 +891,11 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
+    { /* refill with pair p+2; the row offset is uniform, the tail re-reads the last pair */               \
+      const char* nrow = frame_base + (size_t)(2 * min(p + 2, plast)) * rs;                                \
+      CA = ld_stream(nrow, coff);                                                                          \
+      CB = ld_stream(nrow + rs, coff);                                                                     \
+    }                                                                                                      \
     if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
       if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
       if (ey) NEXAR_ACCUM(acc1, ey)                                                                      \
@@ -965,9 +972,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   }
 
     for (int p = p0; p <= plast; ++p) {
-      NEXAR_PAIR(a0, b0, a1, b1)
+      NEXAR_PAIR(a0, b0)
       if (++p > plast) break;
-      NEXAR_PAIR(a1, b1, a0, b0)
+      NEXAR_PAIR(a1, b1)
     }
 #undef NEXAR_PAIR
 #undef NEXAR_ACCUM
