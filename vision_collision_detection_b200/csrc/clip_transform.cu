@@ -742,6 +742,9 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 #ifndef NEXAR_STAGES
 #define NEXAR_STAGES 6  // row pairs in flight per CTA in the TMA ring
 #endif
+#ifndef NEXAR_RSETS
+#define NEXAR_RSETS 2  // register sets of row pairs per thread (prefetch distance in pairs)
+#endif
 #ifndef NEXAR_LOOKAHEAD
 #define NEXAR_LOOKAHEAD 4
 #endif
@@ -840,6 +843,14 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       a1 = ld_stream(nrow, coff);
       b1 = ld_stream(nrow + rs, coff);
     }
+#if NEXAR_RSETS == 3
+    uint4 a2, b2;
+    {
+      const char* nrow = frame_base + (size_t)(2 * min(p0 + 2, plast)) * rs;
+      a2 = ld_stream(nrow, coff);
+      b2 = ld_stream(nrow + rs, coff);
+    }
+#endif
     uint4 e_nx = __ldg(P.pairs + p0);
     const uint4* tp = P.pairs + p0 + 1;
     if (tid < 32) {
@@ -892,7 +903,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
     { /* refill with pair p+2; the row offset is uniform, the tail re-reads the last pair */               \
-      const char* nrow = frame_base + (size_t)(2 * min(p + 2, plast)) * rs;                                \
+      const char* nrow = frame_base + (size_t)(2 * min(p + NEXAR_RSETS, plast)) * rs;                      \
       CA = ld_stream(nrow, coff);                                                                          \
       CB = ld_stream(nrow + rs, coff);                                                                     \
     }                                                                                                      \
@@ -912,6 +923,13 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       const bool s1 = (ez & NEXAR_E_SLOT) != 0u;                                                          \
       if (row >= i0 && row < i1) {                                                                         \
         if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
+        if (tid == 0) { /* once per output row (~S/2 pairs): push the next 4 pairs, LA ahead, into L2 */    \
+          const int q0 = p + 1 + LA;                                                                       \
+          if (q0 <= plast) {                                                                               \
+            const int64_t o0 = (int64_t)(2 * q0) * rs;                                                     \
+            l2_prefetch_bulk(frame_base + o0, (unsigned)min((int64_t)8 * rs, (int64_t)P.src_h * rs - o0)); \
+          }                                                                                                \
+        }                                                                                                  \
         __syncthreads();                                                                                   \
         if (hth) {                                                                                         \
           const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
@@ -962,19 +980,16 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                         \
       }                                                                                                    \
     }                                                                                                      \
-    if ((p & 3) == 3 && tid < 32) { /* warp 0: next 4 pairs, LA ahead, into L2 */                          \
-      const int q0 = p + 1 + LA;                                                                           \
-      if (tid == 0 && q0 <= plast) {                                                                       \
-        const int64_t o0 = (int64_t)(2 * q0) * rs;                                                         \
-        l2_prefetch_bulk(frame_base + o0, (unsigned)min((int64_t)8 * rs, (int64_t)P.src_h * rs - o0));     \
-      }                                                                                                    \
-    }                                                                                                      \
   }
 
     for (int p = p0; p <= plast; ++p) {
       NEXAR_PAIR(a0, b0)
       if (++p > plast) break;
       NEXAR_PAIR(a1, b1)
+#if NEXAR_RSETS == 3
+      if (++p > plast) break;
+      NEXAR_PAIR(a2, b2)
+#endif
     }
 #undef NEXAR_PAIR
 #undef NEXAR_ACCUM
