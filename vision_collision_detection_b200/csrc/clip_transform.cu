@@ -1643,7 +1643,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     K.pass = 0;
     const bool use_tma = g_resize_variant == 3;
     const int ng = (kx + 1 + 3) / 4;
-    const int nt_fast = need_threads <= 256 ? 256 : 384;
+    const int nt_fast = need_threads <= 256 ? 256 : need_threads <= 320 ? 320 : 384;
     const size_t smem_fast = smem + (size_t)ng * nt_fast * 16;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
     const size_t stage_bytes = 2 * (size_t)P.src_w * 3;
     const int ns = need_threads <= 256 ? NEXAR_STAGES : (stage_bytes > 8192 ? 4 : NEXAR_STAGES);
@@ -1673,6 +1673,8 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
       }
     } else if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB) else NEXAR_FAST(20, 256, 2)
+    } else if (need_threads <= 320) {
+      if (kx == 10) NEXAR_FAST(10, 320, 2) else if (kx == 14) NEXAR_FAST(14, 320, 2) else NEXAR_FAST(20, 320, 2)
     } else {
       if (kx == 10) NEXAR_FAST(10, 384, 2) else if (kx == 14) NEXAR_FAST(14, 384, 2) else NEXAR_FAST(20, 384, 2)
     }
