@@ -836,13 +836,13 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const unsigned vbytes = (unsigned)vstride * 2u;
     unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
 
-    uint4 a0 = ld_stream(frame_base + (size_t)(2 * p0) * rs, coff), b0 = ld_stream(frame_base + (size_t)(2 * p0 + 1) * rs, coff);
-    uint4 a1, b1;
-    {
-      const char* nrow = frame_base + (size_t)(2 * min(p0 + 1, plast)) * rs;
-      a1 = ld_stream(nrow, coff);
-      b1 = ld_stream(nrow + rs, coff);
-    }
+    // a frame is < 4 GB: rows are addressed by a uniform 32-bit byte offset from this thread's column base
+    const char* const col_base = frame_base + coff;
+    const unsigned step = 2u * rs, ulast = (unsigned)(2 * plast) * rs;
+    unsigned unext = (unsigned)(2 * p0) * rs;
+    uint4 a0 = ld_stream(col_base, unext), b0 = ld_stream(col_base, unext + rs);
+    unext = min(unext + step, ulast);
+    uint4 a1 = ld_stream(col_base, unext), b1 = ld_stream(col_base, unext + rs);
 #if NEXAR_RSETS == 3
     uint4 a2, b2;
     {
@@ -902,10 +902,10 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
-    { /* refill with pair p+2; the row offset is uniform, the tail re-reads the last pair */               \
-      const char* nrow = frame_base + (size_t)(2 * min(p + NEXAR_RSETS, plast)) * rs;                      \
-      CA = ld_stream(nrow, coff);                                                                          \
-      CB = ld_stream(nrow + rs, coff);                                                                     \
+    { /* refill with pair p+2: running 32-bit row offset (uniform), the tail re-reads the last pair */     \
+      unext = min(unext + step, ulast);                                                                    \
+      CA = ld_stream(col_base, unext);                                                                     \
+      CB = ld_stream(col_base, unext + rs);                                                                \
     }                                                                                                      \
     if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
       if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
