@@ -816,9 +816,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
     const float post = scale * (1.0f / 128.0f);
-    // where this thread's pixel goes (row term added per output row): intermediate (augmented clips) or dst
-    char* const optr = aug ? (char*)(A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0))
-                           : (char*)A.dst + (dbase + (int64_t)xo * A.sx) * (int64_t)sizeof(DstT);
+    // where this frame's pixels go (uniform base; the per-thread column and the row are added per output row)
+    float4* const ibase = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;
+    DstT* const obase = (DstT*)A.dst + dbase;
 
     // ---- vertical pass state ----
     const int sh = P.shift - 7;
@@ -868,14 +868,16 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], ACC[4 * q + 3]); \
     }                                                        \
   }
-#define NEXAR_ACCUM_BEGIN(ACC, WV)                  \
-  {                                                 \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
-      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], rnd);   \
-      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], rnd);   \
-      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], rnd);   \
-      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], rnd);   \
-    }                                               \
+#define NEXAR_ACCUM_BEGIN(ACC, WV)                                                   \
+  {                                                                                  \
+    unsigned wv_; /* pin the tap pair in ONE vector register (else it is re-materialised per accumulator) */ \
+    asm volatile("mov.b32 %0, %1;" : "=r"(wv_) : "r"(WV));                           \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                  \
+      ACC[4 * q + 0] = __dp2a_lo(wv_, lo[q], rnd);                                   \
+      ACC[4 * q + 1] = __dp2a_hi(wv_, lo[q], rnd);                                   \
+      ACC[4 * q + 2] = __dp2a_lo(wv_, hi[q], rnd);                                   \
+      ACC[4 * q + 3] = __dp2a_hi(wv_, hi[q], rnd);                                   \
+    }                                                                                \
   }
 #define NEXAR_STAGE(ACC)                                                                      \
   {                                                                                           \
@@ -960,9 +962,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
             g = clamp01(__fmul_rn(bright, g));                                                             \
             bl = clamp01(__fmul_rn(bright, bl));                                                           \
             gsum += gray_of(r, g, bl);                                                                     \
-            ((float4*)optr)[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                              \
+            ibase[y * A.bw + xo] = make_float4(r, g, bl, 0.0f);                                            \
           } else {                                                                                         \
-            DstT* const o = (DstT*)optr + (int64_t)y * A.sy;                                               \
+            DstT* const o = obase + ((int64_t)y * A.sy + (int64_t)xo * A.sx);                              \
             if (A.normalize) {                                                                             \
               r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
               g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
