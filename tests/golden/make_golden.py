@@ -136,6 +136,12 @@ def main():
     special["r11_random"] = tft.transforms[1](resized, use_letterbox=False).numpy()
     random.seed(11)
     meta["r11_random_left"] = random.randint(0, resized.shape[-1] - 56)  # h == cs -> no 'top' draw
+    # the never-called factory's default forward: short-side resize, then a SECOND antialiased resize (letterbox)
+    tfd = ref.create_video_transform(mode="val", min_size=40, crop_size=56)
+    special["singular_val_40_56"] = tfd(video).numpy()
+    tfd = ref.create_video_transform(mode="train", min_size=40, max_size=None, crop_size=56, horizontal_flip_prob=1.0)
+    random.seed(5)
+    special["singular_train_flip_40_56"] = tfd(video).numpy()
     np.savez_compressed(os.path.join(HERE, "golden_special.npz"), **special)
 
     # letterbox geometry table: measured from the reference on all-ones inputs ---

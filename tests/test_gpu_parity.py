@@ -122,6 +122,19 @@ def test_resize_crop_variant():
     assert np.abs(out - sp["r11_random"]).max() <= TOL_BEFORE
 
 
+def test_singular_factory_default_two_pass():
+    """create_video_transform's default forward chains two antialiased resizes (nexar_video_aug.py:407-463)."""
+    from vision_collision_detection_b200 import create_video_transform
+    from vision_collision_detection_b200.synth import make_clip_np
+    sp = special()
+    video = torch.from_numpy(make_clip_np(2, 96, 160, 53, "dashcam")).permute(3, 0, 1, 2)
+    tf = create_video_transform(mode="val", min_size=40, crop_size=56)
+    assert np.abs(tf(video).numpy() - sp["singular_val_40_56"]).max() <= TOL_AFTER
+    tf = create_video_transform(mode="train", min_size=40, max_size=None, crop_size=56, horizontal_flip_prob=1.0)
+    random.seed(5)
+    assert np.abs(tf(video).numpy() - sp["singular_train_flip_40_56"]).max() <= TOL_AFTER
+
+
 def test_bf16_output_and_layouts():
     c = load_case("custom_small_s2")
     want = torch.from_numpy(c["out"])

@@ -115,20 +115,28 @@ class GpuVideoTransform(nn.Module):
         cs = self.crop_size
         if self.resize_short_side is None:
             return eng.letterbox_plan(h, w, cs, src_dtype)
-        rh, rw = self._resized_hw(h, w)
         if self.use_letterbox:
-            # resize to (rh, rw), then letterbox that into cs: two antialiased passes in the
-            # reference; on the GPU this variant is served by composing the geometry only when
-            # the second pass is the identity (rh or rw == cs and the other <= cs).
-            g = _lib.letterbox_geometry(rh, rw, cs)
-            if (g.resize_h, g.resize_w) != (rh, rw):
-                raise NotImplementedError(
-                    "create_video_transform(use_letterbox=True) needs two chained antialiased resizes "
-                    f"({h}x{w} -> {rh}x{rw} -> {g.resize_h}x{g.resize_w}); use create_video_transforms, "
-                    "which every reference call site uses")
-            geom = _lib.Geometry(h, w, cs, rh, rw, g.off_y, g.off_x)
-            return eng.plan(geom, _SRC[src_dtype])
+            raise RuntimeError("two-pass variant: handled by _forward_two_pass")
         return eng.resize_crop_plan(h, w, self.resize_short_side, cs, src_dtype)
+
+    def _forward_two_pass(self, eng, frames, offsets, n_clips, t_out, packed, any_flags, out, strides):
+        """The never-called factory's default forward (nexar_video_aug.py:407-463): an antialiased short-side
+        resize followed by a SECOND antialiased resize inside crop_tensor(use_letterbox=True).  Pass 1 writes
+        the [0,1] float frames of size (rh, rw) on a square scratch canvas; pass 2 letterboxes those float
+        frames (strided rows) and applies flip / augmentation / normalisation."""
+        h, w = frames.shape[2], frames.shape[3]
+        rh, rw = self._resized_hw(h, w)
+        cm = max(rh, rw)
+        plan1 = eng.plan(_lib.Geometry(h, w, cm, rh, rw, 0, 0), _SRC[frames.dtype])
+        mid, mid_strides = _alloc_out("BTHWC", n_clips, t_out, cm, torch.float32, frames.device)
+        neutral, _ = pack_clip_params([{"flip": False, "aug": None}] * n_clips, cm, None)
+        eng.run(plan1, frames, offsets, n_clips, t_out, eng.upload_params(neutral), 0, mid, mid_strides,
+                False, self.video_mean, self.video_std)
+        plan2 = eng.plan(_lib.letterbox_geometry(rh, rw, self.crop_size), _lib.SRC_F32)
+        offsets2 = eng.contiguous_offsets(n_clips * t_out, cm * cm * 3 * 4)
+        eng.run(plan2, mid, offsets2, n_clips, t_out, eng.upload_params(packed), any_flags, out, strides,
+                self.normalize, self.video_mean, self.video_std, src_row_stride=cm * 3 * 4)
+        return out
 
     # -- batch entry point -------------------------------------------------------------
     @torch.no_grad()
@@ -164,7 +172,8 @@ class GpuVideoTransform(nn.Module):
             raise ValueError("one parameter record per clip is required")
         self.last_params = params
         packed, any_flags = pack_clip_params(params, self.crop_size, self.video_aug)
-        plan = self._plan(eng, h, w, frames.dtype)
+        two_pass = self.resize_short_side is not None and self.use_letterbox
+        plan = None if two_pass else self._plan(eng, h, w, frames.dtype)
         dt = out_dtype or self.out_dtype
         if out is None:
             out, strides = _alloc_out(layout, n_clips, t_out, self.crop_size, dt, frames.device)
@@ -172,6 +181,8 @@ class GpuVideoTransform(nn.Module):
             probe, strides = _alloc_out(layout, n_clips, t_out, self.crop_size, out.dtype, "meta")
             if tuple(out.shape) != tuple(probe.shape) or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous {tuple(probe.shape)} tensor for layout {layout}")
+        if two_pass:
+            return self._forward_two_pass(eng, frames, offsets, n_clips, t_out, packed, any_flags, out, strides)
         pdev = eng.upload_params(packed)
         eng.run(plan, frames, offsets, n_clips, t_out, pdev, any_flags, out, strides,
                 self.normalize, self.video_mean, self.video_std)
