@@ -166,6 +166,23 @@ def test_frame_gather_equals_copy():
     assert torch.equal(a, b)
 
 
+def test_model_input_fast_path_equals_subsampled_full_result():
+    """F2: only the frames the model keeps (nexar_arch.py:411-415), written frame-major."""
+    c = load_case("custom_small_s3")
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = make_clip_np(12, 96, 160, 77, "dashcam")
+    tf = _tf(c["kwargs"])
+    frames = torch.from_numpy(np.stack([clip, clip[::-1].copy()])).cuda()
+    recs = [dict(c["params"], crop=None), dict(c["params"], crop=None, flip=not c["params"]["flip"])]
+    full = tf.forward_batch(frames, params=recs)                          # [2,3,12,cs,cs]
+    fast = tf.forward_model_input(frames, params=recs)                    # [2,6,3,cs,cs]
+    assert tuple(fast.shape) == (2, 6, 3, 56, 56)
+    same = bool(torch.equal(fast.permute(0, 2, 1, 3, 4), full[:, :, ::2]))
+    assert same
+    short = tf.forward_model_input(frames[:, :8], params=recs)            # T <= 10: nothing is dropped
+    assert tuple(short.shape) == (2, 8, 3, 56, 56)
+
+
 def test_full_size_properties():
     """BASELINE cfg2 frame size (720p -> 224): size-independent properties on the device."""
     from vision_collision_detection_b200.synth import make_clip_torch
@@ -213,3 +230,18 @@ def test_fast_and_general_resize_kernels_agree(name, bands):
     assert np.abs(fast - c["out"]).max() <= tol
     assert np.abs(fast - general).max() <= 2.5e-4      # fixed-point budget: < 3e-5 of full scale, /0.225
     assert np.array_equal(tma, fast)
+
+
+@pytest.mark.parametrize("h,w,cs", [(720, 1280, 448), (480, 640, 224), (360, 640, 224), (1080, 1920, 320),
+                                    (2160, 3840, 224), (720, 1280, 112), (224, 224, 224), (300, 500, 224),
+                                    (1280, 720, 224), (64, 64, 320)])
+def test_geometry_zoo_against_oracle(h, w, cs):
+    """Realistic and awkward geometries (fast kernel, general kernel, up-scale, portrait, 4K), one noise frame each."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = make_clip_np(1, h, w, h + w + cs, "noise")
+    kw = dict(mode="train", crop_size=cs, horizontal_flip_prob=1.0)
+    out = _run(_tf(kw), clip, {"flip": True, "aug": None})
+    cfg = O.TransformConfig(mode="train", crop_size=cs, horizontal_flip_prob=1.0)
+    want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": True, "aug": None})
+    err = float(np.abs(out - want).max())
+    assert err <= TOL_AFTER, err

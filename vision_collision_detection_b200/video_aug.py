@@ -188,6 +188,19 @@ class GpuVideoTransform(nn.Module):
                 self.normalize, self.video_mean, self.video_std)
         return out
 
+    @torch.no_grad()
+    def forward_model_input(self, frames: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None,
+                            out_dtype: Optional[torch.dtype] = None, rng=random) -> torch.Tensor:
+        """Opt-in fast path for the consumer.  ``nexar_arch.EnhancedFrameCNN.forward``
+        keeps every other frame when T > 10 and immediately reshapes to ``[B*T',3,H,W]`` (nexar_arch.py:411-419);
+        this transforms only the frames the model keeps and writes them frame-major: returns ``[B,T',3,cs,cs]``
+        (``.flatten(0,1)`` is the backbone input; ``.permute(0,2,1,3,4)`` is the ``[B,3,T',H,W]`` the model's public
+        signature takes).  Same random decisions per clip as ``forward_batch``; parity mode still produces all T."""
+        b, t = frames.shape[0], frames.shape[1]
+        keep = list(range(0, t, 2)) if t > 10 else list(range(t))
+        index = (torch.arange(b, dtype=torch.int64).view(b, 1) * t + torch.tensor(keep, dtype=torch.int64).view(1, -1))
+        return self.forward_batch(frames, params=params, frame_index=index, layout="BTCHW", out_dtype=out_dtype, rng=rng)
+
     # -- reference-compatible call -----------------------------------------------------
     @torch.no_grad()
     def forward(self, video: torch.Tensor) -> torch.Tensor:
