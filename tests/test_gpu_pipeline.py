@@ -132,3 +132,13 @@ def test_host_pipeline_equals_device_path():
     assert got.dtype == torch.bfloat16 and same
     same = bool(torch.equal(pipe.run(host_in, params=params), want))  # buffers are reusable
     assert same
+    # two batches in flight (the steady state bench.py's e2e measures)
+    host_in2 = pipe.pinned_input()
+    host_in2.copy_(torch.from_numpy(clips[::-1].copy()))
+    want2 = tf.forward_batch(torch.from_numpy(clips[::-1].copy()).cuda(), params=params).cpu()
+    t1 = pipe.submit(host_in, params=params)
+    t2 = pipe.submit(host_in2, params=params)
+    r1 = pipe.wait(t1).clone()
+    r2 = pipe.wait(t2).clone()
+    same = bool(torch.equal(r1, want)) and bool(torch.equal(r2, want2))
+    assert same

@@ -30,22 +30,29 @@ class HostClipPipeline:
                        for _ in range(n_streams)]
         self.dev_out = [torch.empty((self.chunk, 3, frames, cs, cs), dtype=self.out_dtype, device=self.device)
                         for _ in range(n_streams)]
-        self.host_out = torch.empty((n_clips, 3, frames, cs, cs), dtype=self.out_dtype).pin_memory()
+        # two result buffers so that submit() of batch i+1 can overlap the D2H tail of batch i (PCIe is full duplex)
+        self.host_outs = [torch.empty((n_clips, 3, frames, cs, cs), dtype=self.out_dtype).pin_memory() for _ in range(2)]
+        self.host_out = self.host_outs[0]
+        self._done = [[torch.cuda.Event() for _ in range(n_streams)] for _ in range(2)]
+        self._slot = 0
 
     def pinned_input(self) -> torch.Tensor:
         return torch.empty(self.shape, dtype=torch.uint8).pin_memory()
 
     @torch.no_grad()
-    def run(self, host_clips: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None) -> torch.Tensor:
-        """host_clips: pinned uint8 [B,T,H,W,3].  Returns the pinned [B,3,T,cs,cs] result (valid on return)."""
+    def submit(self, host_clips: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None) -> int:
+        """Enqueue one batch (pinned uint8 [B,T,H,W,3]); returns a ticket for ``wait``.  At most two batches may be
+        in flight; the input buffer must stay untouched until its ticket has been waited for."""
         if tuple(host_clips.shape) != self.shape or host_clips.dtype != torch.uint8:
             raise ValueError(f"expected uint8 {self.shape}")
         n = self.shape[0]
         if params is None:
             params = self.tf.sample_params(n, self.shape[2], self.shape[3])
-        cur = torch.cuda.current_stream(self.device)
-        for s in self.streams:
-            s.wait_stream(cur)
+        slot = self._slot
+        self._slot ^= 1
+        host_out = self.host_outs[slot]
+        # inputs and outputs are host buffers: nothing to order against the caller's stream, and consecutive
+        # batches may overlap freely (each side stream is in-order, so its staging buffers are reused safely)
         for k, lo in enumerate(range(0, n, self.chunk)):
             hi = min(n, lo + self.chunk)
             i = k % len(self.streams)
@@ -54,8 +61,18 @@ class HostClipPipeline:
                 din.copy_(host_clips[lo:hi], non_blocking=True)
                 dout = self.dev_out[i][: hi - lo]
                 self.tf.forward_batch(din, params=params[lo:hi], out=dout, engine=self.engines[i])
-                self.host_out[lo:hi].copy_(dout, non_blocking=True)
-        for s in self.streams:
-            cur.wait_stream(s)
-        cur.synchronize()
-        return self.host_out
+                host_out[lo:hi].copy_(dout, non_blocking=True)
+        for i, s in enumerate(self.streams):
+            self._done[slot][i].record(s)
+        return slot
+
+    def wait(self, ticket: int) -> torch.Tensor:
+        """Block until the batch behind ``ticket`` is complete; returns its pinned [B,3,T,cs,cs] result."""
+        for ev in self._done[ticket]:
+            ev.synchronize()
+        return self.host_outs[ticket]
+
+    @torch.no_grad()
+    def run(self, host_clips: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None) -> torch.Tensor:
+        """host_clips: pinned uint8 [B,T,H,W,3].  Returns the pinned [B,3,T,cs,cs] result (valid on return)."""
+        return self.wait(self.submit(host_clips, params))
