@@ -245,3 +245,46 @@ def test_geometry_zoo_against_oracle(h, w, cs):
     want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": True, "aug": None})
     err = float(np.abs(out - want).max())
     assert err <= TOL_AFTER, err
+
+
+def test_gaussian_noise_is_statistically_right():
+    """nexar_video_aug.py:244-246: clamp(frame + randn * level, 0, 1).  torch's generator cannot be matched bit for
+    bit on the device, so the check is statistical: zero mean, sigma == noise_level, per-frame independence."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = np.full((3, 96, 160, 3), 128, np.uint8)                     # mid-gray: the clamp never bites at sigma 0.05
+    base = dict(mode="train", crop_size=64, normalize=False, horizontal_flip_prob=0.0, enable_custom_augmentation=True,
+                brightness_range=(1, 1), contrast_range=(1, 1), saturation_range=(1, 1), hue_range=(0, 0),
+                rotation_range=(0, 0), scale_range=(1, 1), shear_range=(0, 0), translate_range=(0, 0))
+    random.seed(0)
+    clean = _tf(base)(torch.from_numpy(clip).permute(3, 0, 1, 2)).numpy()
+    random.seed(0)
+    noisy = _tf(dict(base, noise_level=0.05))(torch.from_numpy(clip).permute(3, 0, 1, 2)).numpy()
+    content = (slice(None), slice(None), slice(14, 50), slice(None))   # letterbox content rows of 96x160 -> 64
+    d = (noisy - clean)[content]
+    assert abs(float(d.mean())) < 2e-3
+    assert abs(float(d.std()) - 0.05) < 2.5e-3
+    assert abs(float(np.corrcoef(d[:, 0].ravel(), d[:, 1].ravel())[0, 1])) < 0.05     # frames get independent noise
+    assert abs(float(np.corrcoef(d[0].ravel(), d[1].ravel())[0, 1])) < 0.05           # and so do channels
+    pad = (noisy - clean)[:, :, :14]                                    # pad rows: clamp(0 + n, 0, 1) keeps the positive half
+    assert float(pad.min()) >= 0.0 and 0.015 < float(pad.mean()) < 0.025
+
+
+def test_extreme_parameters_against_oracle():
+    """Hue at +-0.5, strong rotation / scale / shear / translation, brightness clamp, zero saturation."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = make_clip_np(2, 96, 160, 91, "dashcam")
+    cfg = O.TransformConfig(mode="train", crop_size=64, enable_custom_augmentation=True, aug=O.AugConfig())
+    kw = dict(mode="train", crop_size=64, enable_custom_augmentation=True)
+    for k, aug in enumerate([
+        dict(brightness=1.9, contrast=0.2, saturation=0.0, hue=0.5, rotation=170.0, scale=0.5, shear=25.0, translate_x=20.0, translate_y=-13.0),
+        dict(brightness=0.1, contrast=2.5, saturation=3.0, hue=-0.5, rotation=-90.0, scale=2.0, shear=-40.0, translate_x=-31.5, translate_y=7.25),
+        dict(brightness=1.0, contrast=1.0, saturation=1.0, hue=0.0, rotation=0.0, scale=1.0, shear=0.0, translate_x=0.0, translate_y=0.0),
+    ]):
+        p = dict(aug, apply_affine=any(aug[n] != d for n, d in (("rotation", 0), ("scale", 1), ("shear", 0), ("translate_x", 0), ("translate_y", 0))),
+                 apply_grayscale=False, apply_noise=False, apply_blur=False, apply_cutout=False,
+                 apply_color_inversion=bool(k == 1), apply_solarization=bool(k == 0), apply_posterization=False)
+        params = {"flip": bool(k & 1), "aug": p}
+        out = _run(_tf(kw), clip, params)
+        want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, params)
+        err = float(np.abs(out - want).max())
+        assert err <= TOL_AFTER, (k, err)

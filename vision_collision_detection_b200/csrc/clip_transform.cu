@@ -1368,7 +1368,10 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant_
 // [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them).
 // The result is stored RELATIVE to the pad colour, so that K3 can treat pad neighbours as zeros.
 constexpr int kColourPerThread = 4;
-__global__ void __launch_bounds__(256) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+#ifndef NEXAR_COL_MINB
+#define NEXAR_COL_MINB 6
+#endif
+__global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   const int frame = blockIdx.y;
   const float4* fi4 = (const float4*)(A.finfo + frame);
   const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, hue, -
@@ -1446,10 +1449,16 @@ __device__ __forceinline__ void point_effects(float& r, float& g, float& b, cons
 // content pixel: four unconditional loads; otherwise the general path, which clamps the four addresses
 // into the content box and zeroes the weights of neighbours that are pad or outside the canvas (the
 // intermediate is stored relative to the pad colour, so pad neighbours contribute through the mask only).
-constexpr int kGeoRows = 4;
+#ifndef NEXAR_GEO_ROWS
+#define NEXAR_GEO_ROWS 4
+#endif
+constexpr int kGeoRows = NEXAR_GEO_ROWS;  // rows per thread; the CTA tile is 32 x (8 * kGeoRows)
 enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
+#ifndef NEXAR_GEO_MINB
+#define NEXAR_GEO_MINB 8  // measured: 32 registers / 8 CTAs per SM beats 48 / 5 (the gather is latency-bound)
+#endif
 template <typename DstT>
-__global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   __shared__ int cls_s[kGeoRows];
   const int frame = blockIdx.z;
   const float4* fi4 = (const float4*)(A.finfo + frame);
@@ -1463,7 +1472,7 @@ __global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ D
   struct { int by0, by1, bx0, bx1; } B = {bx.x, bx.y, bx.z, bx.w};
   const int cs = P.cs;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = blockIdx.x * 32 + tx, ybase = blockIdx.y * 32 + ty;
+  const int x = blockIdx.x * 32 + tx, ybase = blockIdx.y * (8 * kGeoRows) + ty;
   const float half = (float)cs * 0.5f, fcs = (float)cs;
   const bool affine = (flags & NEXAR_AFFINE) != 0u;
   const float g0 = q2.x, g1 = q2.y, g2 = q2.z, g3 = q2.w, g4 = q3.x, g5 = q3.y;
@@ -1474,7 +1483,7 @@ __global__ void __launch_bounds__(256) geometry_kernel(const __grid_constant__ D
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float xb = (float)min((int)blockIdx.x * 32 + (c & 1) * 31, cs - 1) - half + 0.5f;
-        const float yb = (float)min((int)blockIdx.y * 32 + 8 * (int)threadIdx.x + (c >> 1) * 7, cs - 1) - half + 0.5f;
+        const float yb = (float)min((int)blockIdx.y * (8 * kGeoRows) + 8 * (int)threadIdx.x + (c >> 1) * 7, cs - 1) - half + 0.5f;
         const float sx = fmaf(fmaf(yb, g1, xb * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
         const float sy = fmaf(fmaf(yb, g4, xb * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
         xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
@@ -1718,7 +1727,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const int cs = P.cs;
     frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
     colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
-    geometry_kernel<DstT><<<dim3((cs + 31) / 32, (cs + 31) / 32, nf), 256, 0, st>>>(P, K);
+    geometry_kernel<DstT><<<dim3((cs + 31) / 32, (cs + 8 * kGeoRows - 1) / (8 * kGeoRows), nf), 256, 0, st>>>(P, K);
     g_launches += 3;
     if (blur_mode) {
       blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
