@@ -259,13 +259,13 @@ def test_gaussian_noise_is_statistically_right():
     clean = _tf(base)(torch.from_numpy(clip).permute(3, 0, 1, 2)).numpy()
     random.seed(0)
     noisy = _tf(dict(base, noise_level=0.05))(torch.from_numpy(clip).permute(3, 0, 1, 2)).numpy()
-    content = (slice(None), slice(None), slice(14, 50), slice(None))   # letterbox content rows of 96x160 -> 64
+    content = (slice(None), slice(None), slice(13, 51), slice(None))   # letterbox content rows of 96x160 -> 64 (38 rows, pad 13)
     d = (noisy - clean)[content]
     assert abs(float(d.mean())) < 2e-3
     assert abs(float(d.std()) - 0.05) < 2.5e-3
     assert abs(float(np.corrcoef(d[:, 0].ravel(), d[:, 1].ravel())[0, 1])) < 0.05     # frames get independent noise
     assert abs(float(np.corrcoef(d[0].ravel(), d[1].ravel())[0, 1])) < 0.05           # and so do channels
-    pad = (noisy - clean)[:, :, :14]                                    # pad rows: clamp(0 + n, 0, 1) keeps the positive half
+    pad = (noisy - clean)[:, :, :13]                                    # pad rows: clamp(0 + n, 0, 1) keeps the positive half
     assert float(pad.min()) >= 0.0 and 0.015 < float(pad.mean()) < 0.025
 
 
