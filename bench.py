@@ -340,7 +340,7 @@ def main():
             roof = {"bound": "hbm", "kernel": "resize (K1)", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "frac_of_8TBs_nominal": ach / 8000.0, "peak_kind": peak_kind,
                     "kernel_ms": k1_ms_avg, "kernel_share_of_step": k1_ms_avg / ms_step,
-                    "algorithmic_bytes_per_launch": k1_bytes, "traffic": ncu_traffic(args.mode),
+                    "algorithmic_bytes_per_launch": k1_bytes, "traffic": ncu_traffic(args.mode) if (args.workload == "cfg2" and args.out_dtype == "bf16") else None,
                     "step_achieved_GBs": b * per_clip / (ms_step * 1e-3) / 1e9}
         cpu = None
         if not args.no_cpu_baseline:
