@@ -64,6 +64,8 @@ class NexarError(RuntimeError):
 def needs_build() -> bool:
     if not os.path.isfile(LIB_PATH):
         return True
+    if os.environ.get("NEXAR_LIB"):      # an experiment build is used as it is, never rebuilt from the current sources
+        return False
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS if os.path.isfile(s))
 

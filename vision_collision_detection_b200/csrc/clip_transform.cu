@@ -61,7 +61,7 @@ struct DevPlan {
   const uint4* pairs;      // [n_pairs] {w slot0, w slot1, w slot2 (u16x2: row 2p | row 2p+1 << 16), emit (count | first_row << 2)}
   int n_pairs, shift;      // weights are round(w * 2^shift), every row sums to exactly 2^shift
   const int* xstart_al;    // [rw] even-aligned first tap
-  const float* xwt_al;     // [rw][kx_al] taps shifted to the aligned start
+  const unsigned* xw16;    // [rw][kx_al / 2] the same taps in 15-bit fixed point, two per word: lo bytes | hi bytes << 16 (dp2a operand)
   int kx_al;
 };
 
@@ -76,6 +76,7 @@ struct NexarPlan {
   std::vector<uint4> pairs;
   std::vector<int> xstart_al;
   std::vector<float> xwt_al;
+  std::vector<unsigned> xw16;
 };
 
 // Fixed-point vertical taps for the input-stationary kernel.  The triangle filter of a >= 2x
@@ -158,6 +159,25 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
     const int xs = p->xstart[j], al = xs & ~1, sh = xs - al;
     p->xstart_al[j] = al;
     for (int k = 0; k < p->xcount[j]; ++k) p->xwt_al[(size_t)j * kx_al + k + sh] = p->xwt[(size_t)j * kx + k];
+  }
+  // The horizontal pass runs on dp2a too: 15-bit taps (rows sum to exactly 2^15) split into low and high bytes,
+  // two taps per word: byte0/1 = low bytes of the even/odd tap, byte2/3 = their high bytes.
+  p->xw16.assign((size_t)g.resize_w * (kx_al / 2), 0u);
+  for (int j = 0; j < g.resize_w; ++j) {
+    std::vector<long> q(kx_al);
+    long sum = 0;
+    int arg = 0;
+    for (int k = 0; k < kx_al; ++k) {
+      q[k] = std::lrint(std::ldexp((double)p->xwt_al[(size_t)j * kx_al + k], 15));
+      sum += q[k];
+      if (q[k] > q[arg]) arg = k;
+    }
+    q[arg] += (1L << 15) - sum;
+    if (q[arg] < 0 || q[arg] > 65535) return false;
+    for (int m = 0; m < kx_al / 2; ++m) {
+      const unsigned e = (unsigned)q[2 * m], o = (unsigned)q[2 * m + 1];
+      p->xw16[(size_t)j * (kx_al / 2) + m] = (e & 255u) | ((o & 255u) << 8) | ((e >> 8) << 16) | ((o >> 8) << 24);
+    }
   }
   return true;
 }
@@ -310,7 +330,7 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   // one device allocation: [pairs (16B aligned)] [ints] [floats]
   const size_t n_pairs_b = p->fast_ok ? p->pairs.size() * sizeof(uint4) : 0;
   const size_t ni = ((size_t)(g->resize_h + g->resize_w) * 2 + (p->fast_ok ? g->resize_w : 0)) * sizeof(int);
-  const size_t nf = ((size_t)g->resize_h * ky + (size_t)g->resize_w * kx + (p->fast_ok ? p->xwt_al.size() : 0)) * sizeof(float);
+  const size_t nf = ((size_t)g->resize_h * ky + (size_t)g->resize_w * kx + (p->fast_ok ? p->xw16.size() : 0)) * sizeof(float);
   p->dev_tables = nullptr;
   cudaError_t e = cudaMalloc(&p->dev_tables, n_pairs_b + ni + nf);
   if (e != cudaSuccess) {
@@ -328,7 +348,7 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   float* hf = (float*)(host.data() + n_pairs_b + ni);
   memcpy(hf, p->ywt.data(), p->ywt.size() * sizeof(float));
   memcpy(hf + p->ywt.size(), p->xwt.data(), p->xwt.size() * sizeof(float));
-  if (p->fast_ok) memcpy(hf + p->ywt.size() + p->xwt.size(), p->xwt_al.data(), p->xwt_al.size() * sizeof(float));
+  if (p->fast_ok) memcpy(hf + p->ywt.size() + p->xwt.size(), p->xw16.data(), p->xw16.size() * sizeof(unsigned));
   e = cudaMemcpy(p->dev_tables, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(p->dev_tables);
@@ -357,7 +377,7 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   d.n_pairs = (int)p->pairs.size() - (p->fast_ok ? 1 : 0);
   d.shift = shift;
   d.xstart_al = p->fast_ok ? di + 2 * g->resize_h + 2 * g->resize_w : nullptr;
-  d.xwt_al = p->fast_ok ? df + p->ywt.size() + p->xwt.size() : nullptr;
+  d.xw16 = p->fast_ok ? (const unsigned*)(df + p->ywt.size() + p->xwt.size()) : nullptr;
   d.kx_al = kx_al;
   *out = p;
   return NEXAR_OK;
@@ -758,7 +778,7 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 #define NEXAR_E_BEGIN1 8u
 #define NEXAR_E_ROWSHIFT 4
 
-template <int KX, int NT, int MINB, typename DstT>
+template <int KX, int NT, int MINB, int RS, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -798,26 +818,21 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const int nj = B.j_hi - B.j_lo;
     const bool hth = tid < nj;
     const int j = B.j_lo + (hth ? tid : 0);
-    // The taps (and, in the last slot, 2^15 * sum(taps)) live in shared memory, NG float4 groups per thread laid
-    // out group-major so that a warp's LDS.128 is conflict-free; this keeps 14+ registers free for the vertical pass.
-    constexpr int NG = (KX + 1 + 3) / 4;
-    float4* const wsm = (float4*)(smem_raw + 2u * (unsigned)vstride * 2u);
+    // The taps live in shared memory as dp2a operands (two 15-bit taps per word, see build_fast_tables), NG uint4
+    // groups per thread laid out group-major so that a warp's LDS.128 is conflict-free.
+    constexpr int NW = KX / 2, NG = (NW + 3) / 4;
+    uint4* const wsm = (uint4*)(smem_raw + 2u * (unsigned)vstride * 2u);
     {
-      float wtmp[4 * NG];
-      float hb = 0.0f;
+      unsigned wtmp[4 * NG];
 #pragma unroll
-      for (int k = 0; k < 4 * NG; ++k) {
-        wtmp[k] = (k < KX && hth) ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
-        hb = fmaf(wtmp[k], 32768.0f, hb);
-      }
-      wtmp[4 * NG - 1] = hb;
+      for (int k = 0; k < 4 * NG; ++k) wtmp[k] = (k < NW && hth) ? P.xw16[(size_t)j * NW + k] : 0u;
 #pragma unroll
-      for (int g = 0; g < NG; ++g) wsm[g * NT + tid] = make_float4(wtmp[4 * g], wtmp[4 * g + 1], wtmp[4 * g + 2], wtmp[4 * g + 3]);
+      for (int g = 0; g < NG; ++g) wsm[g * NT + tid] = make_uint4(wtmp[4 * g], wtmp[4 * g + 1], wtmp[4 * g + 2], wtmp[4 * g + 3]);
     }
     const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
-    const float post = scale * (1.0f / 128.0f);
+    const float post = scale * (1.0f / (128.0f * 32768.0f));
     // where this frame's pixels go (uniform base; the per-thread column and the row are added per output row)
     float4* const ibase = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;
     DstT* const obase = (DstT*)A.dst + dbase;
@@ -832,28 +847,26 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
     const bool vstore = tid < nchunks;
     const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
-    const unsigned rs = (unsigned)A.src_row_stride;  // a frame is < 4 GB: 32-bit offsets from the frame base
-    const unsigned coff = (unsigned)chunk * 16u;
+    // RS > 0: the row stride is a compile-time constant, so every load below is [pointer + immediate]
+    const unsigned rs = RS > 0 ? (unsigned)RS : (unsigned)A.src_row_stride;
     const unsigned vbytes = (unsigned)vstride * 2u;
     unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
 
-    // a frame is < 4 GB: rows are addressed by a uniform 32-bit byte offset from this thread's column base
-    const char* const col_base = frame_base + coff;
-    const unsigned step = 2u * rs, ulast = (unsigned)(2 * plast) * rs;
-    unsigned unext = (unsigned)(2 * p0) * rs;
-    uint4 a0 = ld_stream(col_base, unext), b0 = ld_stream(col_base, unext + rs);
-    unext = min(unext + step, ulast);
-    uint4 a1 = ld_stream(col_base, unext), b1 = ld_stream(col_base, unext + rs);
-#if NEXAR_RSETS == 3
-    uint4 a2, b2;
-    {
-      const char* nrow = frame_base + (size_t)(2 * min(p0 + 2, plast)) * rs;
-      a2 = ld_stream(nrow, coff);
-      b2 = ld_stream(nrow + rs, coff);
+    // this thread's 16 bytes of row 2p (running pointer, advanced once per two pairs); pairs p+2 / p+3 are
+    // fetched at fixed row offsets from it, and nothing is fetched past the band's last pair
+    const char* ptr = frame_base + (size_t)chunk * 16u + (size_t)(2 * p0) * rs;
+    uint4 a0 = ld_stream(ptr, 0u), b0 = ld_stream(ptr, rs);
+    uint4 a1 = a0, b1 = b0;
+    if (p0 + 1 <= plast) {
+      a1 = ld_stream(ptr, 2u * rs);
+      b1 = ld_stream(ptr, 3u * rs);
     }
-#endif
-    uint4 e_nx = __ldg(P.pairs + p0);
-    const uint4* tp = P.pairs + p0 + 1;
+    // the band's control words, staged in shared memory: the loop reads them with a uniform address, one pair ahead
+    uint4* const ctl = (uint4*)(wsm + NG * NT);
+    for (int e = tid; e <= plast - p0 + 1; e += NT) ctl[e] = __ldg(P.pairs + p0 + e);  // table has a spare entry
+    __syncthreads();
+    uint4 e_nx = ctl[0];
+    const uint4* tp = ctl + 1;
     if (tid < 32) {
       const int q0 = p0 + 2, q1 = min(p0 + LA + 3, plast);
       if (tid == 0 && q1 >= q0)
@@ -894,10 +907,10 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
 // One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk.  As soon as their bytes have been
 // interleaved into lo/hi the same registers are refilled with pair p+2 (two register sets ping-pong, so
 // every load has almost two iterations to land).
-#define NEXAR_PAIR(CA, CB)                                                                                 \
+#define NEXAR_PAIR(CA, CB, ROFF)                                                                               \
   {                                                                                                        \
     const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
-    e_nx = __ldg(tp); /* control words of the next pair, one iteration ahead (table has a spare entry) */  \
+    e_nx = *tp; /* control words of the next pair, one iteration ahead (table has a spare entry) */        \
     ++tp;                                                                                                  \
     orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
     unsigned lo[4], hi[4];                                                                                 \
@@ -905,10 +918,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
     lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
     lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
-    { /* refill with pair p+2: running 32-bit row offset (uniform), the tail re-reads the last pair */     \
-      unext = min(unext + step, ulast);                                                                    \
-      CA = ld_stream(col_base, unext);                                                                     \
-      CB = ld_stream(col_base, unext + rs);                                                                \
+    if (p + 2 <= plast) { /* refill with pair p+2 */                                                      \
+      CA = ld_stream(ptr, (unsigned)(ROFF) * rs);                                                          \
+      CB = ld_stream(ptr, (unsigned)(ROFF + 1) * rs);                                                      \
     }                                                                                                      \
     if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
       if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
@@ -936,26 +948,23 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         __syncthreads();                                                                                   \
         if (hth) {                                                                                         \
           const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
-          float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
-          unsigned w0 = src[0], w1 = src[1], w2 = src[2];                                                  \
-          float4 wq = wsm[tid];                                                                            \
-          _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
-            unsigned n0 = 0u, n1 = 0u, n2 = 0u;                                                            \
-            if (k + 2 < KX) { n0 = src[3 * (k >> 1) + 3]; n1 = src[3 * (k >> 1) + 4]; n2 = src[3 * (k >> 1) + 5]; } \
-            const float wa = (k & 2) ? wq.z : wq.x, wb = (k & 2) ? wq.w : wq.y;                            \
-            r = fmaf(wa, magic_lo(w0), r);                                                                 \
-            g = fmaf(wa, magic_hi(w0), g);                                                                 \
-            bl = fmaf(wa, magic_lo(w1), bl);                                                               \
-            r = fmaf(wb, magic_hi(w1), r);                                                                 \
-            g = fmaf(wb, magic_lo(w2), g);                                                                 \
-            bl = fmaf(wb, magic_hi(w2), bl);                                                               \
-            w0 = n0; w1 = n1; w2 = n2;                                                                     \
-            if ((k & 2) && (k + 2) / 4 < NG) wq = wsm[((k + 2) / 4) * NT + tid];                           \
+          /* two taps per step: regroup (R0 G0)(B0 R1)(G1 B1) into per-channel pairs, dp2a against the low and */ \
+          /* the high tap bytes; value * 2^15 * sum(taps) = hi * 256 + lo (< 2^31) */                     \
+          unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
+          uint4 wq = wsm[tid];                                                                             \
+          _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
+            const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
+            const unsigned ww = (m & 3) == 0 ? wq.x : (m & 3) == 1 ? wq.y : (m & 3) == 2 ? wq.z : wq.w;    \
+            const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
+                           bb = __byte_perm(w1, w2, 0x7610);                                               \
+            rl = __dp2a_lo(rr, ww, rl); rh = __dp2a_hi(rr, ww, rh);                                        \
+            gl = __dp2a_lo(gg, ww, gl); gh = __dp2a_hi(gg, ww, gh);                                        \
+            bl_ = __dp2a_lo(bb, ww, bl_); bh = __dp2a_hi(bb, ww, bh);                                      \
+            if ((m & 3) == 3 && (m + 1) / 4 < NG) wq = wsm[((m + 1) / 4) * NT + tid];                      \
           }                                                                                                \
-          const float hbias = (KX % 4 == 0) ? wsm[(NG - 1) * NT + tid].w : wq.w;                           \
-          r = (r - hbias) * post;                                                                          \
-          g = (g - hbias) * post;                                                                          \
-          bl = (bl - hbias) * post;                                                                        \
+          float r = (float)(int)(rh * 256u + rl) * post;                                                   \
+          float g = (float)(int)(gh * 256u + gl) * post;                                                   \
+          float bl = (float)(int)(bh * 256u + bl_) * post;                                                 \
           const int y = row + B.oy;                                                                        \
           if (aug) {                                                                                       \
             const float bright = cp->brightness;                                                           \
@@ -986,13 +995,10 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   }
 
     for (int p = p0; p <= plast; ++p) {
-      NEXAR_PAIR(a0, b0)
+      NEXAR_PAIR(a0, b0, 4)
       if (++p > plast) break;
-      NEXAR_PAIR(a1, b1)
-#if NEXAR_RSETS == 3
-      if (++p > plast) break;
-      NEXAR_PAIR(a2, b2)
-#endif
+      NEXAR_PAIR(a1, b1, 6)
+      ptr += 4u * rs;
     }
 #undef NEXAR_PAIR
 #undef NEXAR_ACCUM
@@ -1081,16 +1087,14 @@ resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KAr
     const int nj = B.j_hi - B.j_lo;
     const bool hth = tid < nj;
     const int j = B.j_lo + (hth ? tid : 0);
-    float wx[KX];
+    constexpr int NW = KX / 2;  // taps as dp2a operands (two 15-bit taps per word), in registers
+    unsigned wx[NW];
 #pragma unroll
-    for (int k = 0; k < KX; ++k) wx[k] = hth ? P.xwt_al[(size_t)j * P.kx_al + k] : 0.0f;
-    float hbias = 0.0f;
-#pragma unroll
-    for (int k = 0; k < KX; ++k) hbias = fmaf(wx[k], 32768.0f, hbias);
+    for (int k = 0; k < NW; ++k) wx[k] = hth ? P.xw16[(size_t)j * NW + k] : 0u;
     const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
     int xo = j + B.ox;
     if (flip) xo = P.cs - 1 - xo;
-    const float post = scale * (1.0f / 128.0f);
+    const float post = scale * (1.0f / (128.0f * 32768.0f));
     // where this thread's pixel goes (row term added per output row): intermediate (augmented clips) or dst
     char* const optr = aug ? (char*)(A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0))
                            : (char*)A.dst + (dbase + (int64_t)xo * A.sx) * (int64_t)sizeof(DstT);
@@ -1215,22 +1219,18 @@ resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KAr
         __syncthreads();                                                                                   \
         if (hth) {                                                                                         \
           const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
-          float r = 0.0f, g = 0.0f, bl = 0.0f;                                                             \
-          unsigned w0 = src[0], w1 = src[1], w2 = src[2];                                                  \
-          _Pragma("unroll") for (int k = 0; k < KX; k += 2) {                                              \
-            unsigned n0 = 0u, n1 = 0u, n2 = 0u;                                                            \
-            if (k + 2 < KX) { n0 = src[3 * (k >> 1) + 3]; n1 = src[3 * (k >> 1) + 4]; n2 = src[3 * (k >> 1) + 5]; } \
-            r = fmaf(wx[k], magic_lo(w0), r);                                                              \
-            g = fmaf(wx[k], magic_hi(w0), g);                                                              \
-            bl = fmaf(wx[k], magic_lo(w1), bl);                                                            \
-            r = fmaf(wx[k + 1], magic_hi(w1), r);                                                          \
-            g = fmaf(wx[k + 1], magic_lo(w2), g);                                                          \
-            bl = fmaf(wx[k + 1], magic_hi(w2), bl);                                                        \
-            w0 = n0; w1 = n1; w2 = n2;                                                                     \
+          unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
+          _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
+            const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
+            const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
+                           bb = __byte_perm(w1, w2, 0x7610);                                               \
+            rl = __dp2a_lo(rr, wx[m], rl); rh = __dp2a_hi(rr, wx[m], rh);                                  \
+            gl = __dp2a_lo(gg, wx[m], gl); gh = __dp2a_hi(gg, wx[m], gh);                                  \
+            bl_ = __dp2a_lo(bb, wx[m], bl_); bh = __dp2a_hi(bb, wx[m], bh);                                \
           }                                                                                                \
-          r = (r - hbias) * post;                                                                          \
-          g = (g - hbias) * post;                                                                          \
-          bl = (bl - hbias) * post;                                                                        \
+          float r = (float)(int)(rh * 256u + rl) * post;                                                   \
+          float g = (float)(int)(gh * 256u + gl) * post;                                                   \
+          float bl = (float)(int)(bh * 256u + bl_) * post;                                                 \
           const int y = row + B.oy;                                                                        \
           if (aug) {                                                                                       \
             const float bright = cp->brightness;                                                           \
@@ -1653,20 +1653,24 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     dim3 grid(nbands, nf);
     K.pass = 0;
     const bool use_tma = g_resize_variant == 3;
-    const int ng = (kx + 1 + 3) / 4;
+    const int ng = (kx / 2 + 3) / 4;
     const int nt_fast = need_threads <= 256 ? 256 : need_threads <= 320 ? 320 : 384;
-    const size_t smem_fast = smem + (size_t)ng * nt_fast * 16;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
+    const size_t smem_fast = smem + (size_t)ng * nt_fast * 16 + (size_t)(P.n_pairs + 1) * 16;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
     const size_t stage_bytes = 2 * (size_t)P.src_w * 3;
     const int ns = need_threads <= 256 ? NEXAR_STAGES : (stage_bytes > 8192 ? 4 : NEXAR_STAGES);
     const size_t smem_tma = smem + ns * stage_bytes + 16 * ns;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
-#define NEXAR_FAST(KXV, NTV, MB)                                                                                 \
+#define NEXAR_FAST_RS(KXV, NTV, MB, RSV)                                                                          \
   {                                                                                                               \
-    auto kern = resize_fast_kernel<KXV, NTV, MB, DstT>;                                                            \
+    auto kern = resize_fast_kernel<KXV, NTV, MB, RSV, DstT>;                                                       \
     if (smem_fast > 48 * 1024)                                                                                    \
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));           \
     kern<<<grid, NTV, smem_fast, st>>>(P, K);                                                                      \
   }
+#define NEXAR_FAST(KXV, NTV, MB) NEXAR_FAST_RS(KXV, NTV, MB, 0)
+// tightly packed 720p / 1080p rows get the row stride as a compile-time constant (immediate load offsets)
+#define NEXAR_FAST_SPEC(KXV, NTV, MB, RSV) \
+  if (a->src_row_stride == RSV) NEXAR_FAST_RS(KXV, NTV, MB, RSV) else NEXAR_FAST_RS(KXV, NTV, MB, 0)
 #define NEXAR_TMA(KXV, NTV, MB, NSV)                                                                              \
   {                                                                                                               \
     auto kern = resize_tma_kernel<KXV, NTV, MB, NSV, DstT>;                                                        \
@@ -1683,13 +1687,15 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
         if (kx == 10) NEXAR_TMA(10, 384, 2, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 384, 2, NEXAR_STAGES) else NEXAR_TMA(20, 384, 2, NEXAR_STAGES)
       }
     } else if (need_threads <= 256) {
-      if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST(14, 256, NEXAR_MINB) else NEXAR_FAST(20, 256, 2)
+      if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST_SPEC(14, 256, NEXAR_MINB, 3840) else NEXAR_FAST(20, 256, 2)
     } else if (need_threads <= 320) {
-      if (kx == 10) NEXAR_FAST(10, 320, 2) else if (kx == 14) NEXAR_FAST(14, 320, 2) else NEXAR_FAST(20, 320, 2)
+      if (kx == 10) NEXAR_FAST_SPEC(10, 320, 2, 3840) else if (kx == 14) NEXAR_FAST(14, 320, 2) else NEXAR_FAST(20, 320, 2)
     } else {
-      if (kx == 10) NEXAR_FAST(10, 384, 2) else if (kx == 14) NEXAR_FAST(14, 384, 2) else NEXAR_FAST(20, 384, 2)
+      if (kx == 10) NEXAR_FAST(10, 384, 2) else if (kx == 14) NEXAR_FAST(14, 384, 2) else NEXAR_FAST_SPEC(20, 384, 2, 5760)
     }
+#undef NEXAR_FAST_SPEC
 #undef NEXAR_FAST
+#undef NEXAR_FAST_RS
 #undef NEXAR_TMA
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
     // fix-up of clips whose maximum was <= 1 (not divided by 255): their values live in [0,1], below the
