@@ -500,6 +500,19 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(void* dst, int64_t idx,
   ((__nv_bfloat16*)dst)[idx] = __float2bfloat16_rn(v);
 }
 
+// same, through an explicit st.global (for pointers whose provenance the compiler cannot see)
+template <typename T>
+__device__ __forceinline__ void store_out_global(T* p, float v);
+template <>
+__device__ __forceinline__ void store_out_global<float>(float* p, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+template <>
+__device__ __forceinline__ void store_out_global<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(h) : "memory");
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1321,7 +1334,9 @@ __device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const
   r = clamp01(__fadd_rn(__fmul_rn(c.saturation, r), gq));
   g = clamp01(__fadd_rn(__fmul_rn(c.saturation, g), gq));
   b = clamp01(__fadd_rn(__fmul_rn(c.saturation, b), gq));
-  hue_shift(r, g, b, c.hue);
+  // hue == 0: torchvision still runs RGB -> HSV -> RGB, which is the identity up to a few ulp (p = v - (max - min) etc.);
+  // the round trip is skipped here (uniform per frame).  Measured against the oracle, which always runs it: < 1e-6.
+  if (c.hue != 0.0f) hue_shift(r, g, b, c.hue);
 }
 
 __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, int frame, int slot, int nbands) {
@@ -1442,148 +1457,168 @@ __device__ __forceinline__ void point_effects(float& r, float& g, float& b, cons
   }
 }
 
-// Thread block = 32 x 32 output pixels of one frame, four rows per thread (rows ty, ty+8, ty+16, ty+24).
-// Each of the four 32 x 8 sub-tiles is classified once from its corners (affine maps are linear, so the
-// corners bound the sub-tile): FILL — maps strictly inside the canvas and entirely into the pad band
-// beside the content: constant pad colour, no memory traffic; INTERIOR — every bilinear neighbour is a
-// content pixel: four unconditional loads; otherwise the general path, which clamps the four addresses
-// into the content box and zeroes the weights of neighbours that are pad or outside the canvas (the
-// intermediate is stored relative to the pad colour, so pad neighbours contribute through the mask only).
+// Every frame of a clip shares the clip's affine map, content box and flags, so the per-pixel geometry (source
+// position, the four neighbour offsets, their weights and the interpolated ones-mask) is computed ONCE and reused
+// for kGeoFrames consecutive frames of the clip; per frame only the pad colour changes.  Thread block = 32 x
+// (8 * kGeoRows) output pixels x kGeoFrames frames; a warp owns a strip of 32 x kGeoRows pixels (consecutive rows,
+// one pixel per thread and row).  The strip is classified once, by every lane identically (no shared memory, no
+// barrier), from the image of its centre and the half extents of an affine map: FILL — maps strictly inside the
+// canvas and entirely into the pad band beside the content: constant pad colour, no memory traffic; INTERIOR — every
+// bilinear neighbour is a content pixel (weights as they are, mask 1); otherwise the four addresses are clamped into
+// the content box and the weights of neighbours that are pad or outside the canvas are zeroed (the intermediate is
+// stored relative to the pad colour, so pad neighbours contribute through the mask only).  All three classes and the
+// no-affine case then run the same per-frame code: out = m * (pad * m + sum(v * w)).
+// Offsets inside one clip of the intermediate and one frame of the destination are 32-bit (checked on the host).
 #ifndef NEXAR_GEO_ROWS
 #define NEXAR_GEO_ROWS 4
 #endif
-constexpr int kGeoRows = NEXAR_GEO_ROWS;  // rows per thread; the CTA tile is 32 x (8 * kGeoRows)
-enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
-#ifndef NEXAR_GEO_MINB
-#define NEXAR_GEO_MINB 8  // measured: 32 registers / 8 CTAs per SM beats 48 / 5 (the gather is latency-bound)
+#ifndef NEXAR_GEO_FRAMES
+#define NEXAR_GEO_FRAMES 4
 #endif
-template <typename DstT>
+constexpr int kGeoRows = NEXAR_GEO_ROWS;      // rows per warp; the CTA tile is 32 x (8 * kGeoRows)
+constexpr int kGeoFrames = NEXAR_GEO_FRAMES;  // frames of one clip per CTA
+enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
+constexpr unsigned kTailFlags = NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT;
+#ifndef NEXAR_GEO_MINB
+#define NEXAR_GEO_MINB 5  // measured (cfg2 custom step): 5 CTAs/SM 0.511 ms, 4: 0.513, 6: 0.517 (spills)
+#endif
+template <typename DstT, bool TAIL>
 __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
-  __shared__ int cls_s[kGeoRows];
-  const int frame = blockIdx.z;
-  const float4* fi4 = (const float4*)(A.finfo + frame);
-  const float4 padv = __ldg(fi4), q2 = __ldg(fi4 + 2), q3 = __ldg(fi4 + 3);
-  const int4 bx = __ldg((const int4*)fi4 + 1);
+  const int nchunk = (A.T + kGeoFrames - 1) / kGeoFrames;
+  const int clip = blockIdx.z / nchunk;
+  const int t0 = (blockIdx.z - clip * nchunk) * kGeoFrames, t1 = min(A.T, t0 + kGeoFrames);
+  const int frame0 = clip * A.T + t0;
+  const float4* fi4 = (const float4*)(A.finfo + frame0);
+  const float4 q3 = __ldg(fi4 + 3);
   const unsigned flags = __float_as_uint(q3.z);
   if (!(flags & NEXAR_AUG)) return;
-  const int clip = frame / A.T;
-  const int t = frame - clip * A.T;
+  const int cs = P.cs;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y0 = blockIdx.y * (8 * kGeoRows) + (threadIdx.x >> 5) * kGeoRows;
+  if (x >= cs || y0 >= cs) return;
+  const float4 q2 = __ldg(fi4 + 2);
+  const int4 bx = __ldg((const int4*)fi4 + 1);
   const NexarClipParams* cp = A.params + clip;   // only the rare tail effects read it
   struct { int by0, by1, bx0, bx1; } B = {bx.x, bx.y, bx.z, bx.w};
-  const int cs = P.cs;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = blockIdx.x * 32 + tx, ybase = blockIdx.y * (8 * kGeoRows) + ty;
   const float half = (float)cs * 0.5f, fcs = (float)cs;
   const bool affine = (flags & NEXAR_AFFINE) != 0u;
   const float g0 = q2.x, g1 = q2.y, g2 = q2.z, g3 = q2.w, g4 = q3.x, g5 = q3.y;
-  if (threadIdx.x < kGeoRows) {
-    int cls = GEO_GENERAL;
-    if (affine) {
-      float ymin = 1e30f, ymax = -1e30f, xmin = 1e30f, xmax = -1e30f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float xb = (float)min((int)blockIdx.x * 32 + (c & 1) * 31, cs - 1) - half + 0.5f;
-        const float yb = (float)min((int)blockIdx.y * (8 * kGeoRows) + 8 * (int)threadIdx.x + (c >> 1) * 7, cs - 1) - half + 0.5f;
-        const float sx = fmaf(fmaf(yb, g1, xb * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
-        const float sy = fmaf(fmaf(yb, g4, xb * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
-        xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
-        ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
-      }
-      // 0.01 px of slack for fp rounding differences between the corner and per-pixel evaluation
-      const bool inside = xmin >= 0.01f && xmax <= fcs - 1.01f && ymin >= 0.01f && ymax <= fcs - 1.01f;
-      const bool above = ymax + 1.01f < (float)B.by0, below = ymin - 0.01f >= (float)B.by1;
-      const bool left = xmax + 1.01f < (float)B.bx0, right = xmin - 0.01f >= (float)B.bx1;
-      const bool interior = xmin >= (float)B.bx0 + 0.01f && xmax <= (float)B.bx1 - 1.01f &&
-                            ymin >= (float)B.by0 + 0.01f && ymax <= (float)B.by1 - 1.01f;
-      cls = (inside && (above || below || left || right)) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
-    }
-    cls_s[threadIdx.x] = cls;
+  int cls = GEO_GENERAL;
+  if (affine) {
+    // image of the strip centre +- the half extents of the strip under the linear part (a superset for strips
+    // that stick out of the canvas); 0.01 px of slack for rounding differences against the per-pixel evaluation
+    const float xc = (float)(blockIdx.x * 32 + 16) - half, yc = (float)y0 + 0.5f * (float)kGeoRows - half;
+    const float sxc = fmaf(fmaf(yc, g1, xc * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float syc = fmaf(fmaf(yc, g4, xc * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float hr = 0.5f * (float)(kGeoRows - 1);
+    const float ex = (15.5f * fabsf(g0) + hr * fabsf(g1)) * half + 0.01f;
+    const float ey = (15.5f * fabsf(g3) + hr * fabsf(g4)) * half + 0.01f;
+    const float xmin = sxc - ex, xmax = sxc + ex, ymin = syc - ey, ymax = syc + ey;
+    const bool inside = xmin >= 0.0f && xmax <= fcs - 1.0f && ymin >= 0.0f && ymax <= fcs - 1.0f;
+    const bool above = ymax + 1.0f < (float)B.by0, below = ymin >= (float)B.by1;
+    const bool left = xmax + 1.0f < (float)B.bx0, right = xmin >= (float)B.bx1;
+    const bool interior = xmin >= (float)B.bx0 && xmax <= (float)B.bx1 - 1.0f && ymin >= (float)B.by0 && ymax <= (float)B.by1 - 1.0f;
+    cls = (inside && (above || below || left || right)) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
   }
-  __syncthreads();
-  if (x >= cs) return;
-  const float4* fr = A.inter + (int64_t)frame * (A.bh * A.bw) - (B.by0 * A.bw + B.bx0);  // indexed by canvas (y, x)
+  const int fstride = A.bh * A.bw;  // float4 elements per intermediate frame
+  const float4* const fr0 = A.inter + (int64_t)frame0 * fstride - (B.by0 * A.bw + B.bx0);  // frame t0, indexed by canvas (y, x)
   const float xb = (float)x - half + 0.5f;
-  DstT* const obase = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t * A.st + (int64_t)x * A.sx);
-  const bool tail_fx = (flags & (NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT)) != 0u;
-  const float ns0 = A.normalize ? A.nscale[0] : 1.0f, ns1 = A.normalize ? A.nscale[1] : 1.0f, ns2 = A.normalize ? A.nscale[2] : 1.0f;
-  const float nb0 = A.normalize ? A.nbias[0] : 0.0f, nb1 = A.normalize ? A.nbias[1] : 0.0f, nb2 = A.normalize ? A.nbias[2] : 0.0f;
-#pragma unroll
+  const float xg0 = xb * g0, xg3 = xb * g3;
+  DstT* const obase0 = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t0 * A.st);
+  const int osy = (int)A.sy, osc = (int)A.sc;
+  const int off0 = y0 * osy + x * (int)A.sx;
+  // TAIL: some clip of the batch has an effect after the affine step (grayscale .. cutout); the common case compiles without them
+  const bool tail_fx = TAIL && (flags & kTailFlags) != 0u;
+  const char* const fr0b = (const char*)fr0;
+  const char* const ob0b = (const char*)obase0;
+  const int64_t fbytes = (int64_t)fstride * 16, stbytes = A.st * (int64_t)sizeof(DstT);
+#pragma unroll 1
   for (int k = 0; k < kGeoRows; ++k) {
-    const int y = ybase + 8 * k;
+    const int y = y0 + k;
     if (y >= cs) break;
-    const int cls = cls_s[k];
-    float r, g, b;
+    // ---- geometry of this pixel, shared by the frames of the clip ----
+    int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+    float w00 = 0.0f, w01 = 0.0f, w10 = 0.0f, w11 = 0.0f, m = 1.0f;
     if (cls == GEO_FILL) {
-      r = padv.x; g = padv.y; b = padv.z;
+      // pad colour only
     } else if (affine) {
       // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
       const float yb = (float)y - half + 0.5f;
-      const float gx = fmaf(yb, g1, xb * g0) + g2;
-      const float gy = fmaf(yb, g4, xb * g3) + g5;
+      const float gx = fmaf(yb, g1, xg0) + g2;
+      const float gy = fmaf(yb, g4, xg3) + g5;
       const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
       const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
       const float x0f = floorf(ix), y0f = floorf(iy);
       const float wx1 = ix - x0f, wy1 = iy - y0f;
       const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
       if (cls == GEO_INTERIOR) {
-        const float4* row0 = fr + (int64_t)((int)y0f * A.bw + (int)x0f);
-        const float4 v00 = __ldg(row0), v01 = __ldg(row0 + 1), v10 = __ldg(row0 + A.bw), v11 = __ldg(row0 + A.bw + 1);
-        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
-        r = padv.x + fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00)));
-        g = padv.y + fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00)));
-        b = padv.z + fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00)));
+        o00 = (int)y0f * A.bw + (int)x0f;
+        o01 = o00 + 1; o10 = o00 + A.bw; o11 = o10 + 1;
+        w00 = wx0 * wy0; w01 = wx1 * wy0; w10 = wx0 * wy1; w11 = wx1 * wy1;
       } else {
         // clamp before the int cast so wild matrices cannot overflow
         const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
-        const int y0 = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
+        const int yq = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
         const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
-        const bool iny0 = (unsigned)y0 < (unsigned)cs, iny1 = (unsigned)(y0 + 1) < (unsigned)cs;
+        const bool iny0 = (unsigned)yq < (unsigned)cs, iny1 = (unsigned)(yq + 1) < (unsigned)cs;
         const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
-        const float m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
+        m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
         const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
-        const bool cy0 = y0 >= B.by0 && y0 < B.by1, cy1 = y0 + 1 >= B.by0 && y0 + 1 < B.by1;
+        const bool cy0 = yq >= B.by0 && yq < B.by1, cy1 = yq + 1 >= B.by0 && yq + 1 < B.by1;
         const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
         const int xc0 = min(max(x0, B.bx0), B.bx1 - 1), xc1 = min(max(x0 + 1, B.bx0), B.bx1 - 1);
-        const int yc0 = min(max(y0, B.by0), B.by1 - 1), yc1 = min(max(y0 + 1, B.by0), B.by1 - 1);
-        const float4* row0 = fr + (int64_t)(yc0 * A.bw);
-        const float4* row1 = fr + (int64_t)(yc1 * A.bw);
-        const float4 v00 = __ldg(row0 + xc0), v01 = __ldg(row0 + xc1), v10 = __ldg(row1 + xc0), v11 = __ldg(row1 + xc1);
-        const float w00 = bx0w * by0w, w01 = bx1w * by0w, w10 = bx0w * by1w, w11 = bx1w * by1w;
-        r = fmaf(padv.x, m, fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00))));
-        g = fmaf(padv.y, m, fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00))));
-        b = fmaf(padv.z, m, fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00))));
-        r *= m;  // img * mask + (1 - mask) * 0
-        g *= m;
-        b *= m;
+        const int yc0 = min(max(yq, B.by0), B.by1 - 1) * A.bw, yc1 = min(max(yq + 1, B.by0), B.by1 - 1) * A.bw;
+        o00 = yc0 + xc0; o01 = yc0 + xc1; o10 = yc1 + xc0; o11 = yc1 + xc1;
+        w00 = bx0w * by0w; w01 = bx1w * by0w; w10 = bx0w * by1w; w11 = bx1w * by1w;
       }
-    } else if (y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1) {
-      const float4 v = __ldg(fr + (int64_t)(y * A.bw + x));
-      r = padv.x + v.x; g = padv.y + v.y; b = padv.z + v.z;
     } else {
-      r = padv.x; g = padv.y; b = padv.z;
+      // no affine: the pixel itself when it is content, the pad colour otherwise
+      const bool in = y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1;
+      o00 = o01 = o10 = o11 = min(max(y, B.by0), B.by1 - 1) * A.bw + min(max(x, B.bx0), B.bx1 - 1);
+      w00 = in ? 1.0f : 0.0f;
     }
-    if (tail_fx) {
-      const int idx = y * cs + x;
-      if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
-      if (flags & NEXAR_NOISE) {
-        const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
-        r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
-        g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
-        b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+    // ---- the frames (fully unrolled).  The per-frame base pointers are made opaque so that every address below
+    // is ONE multiply-add (IMAD.WIDE index * size + base) instead of a 64-bit add chain ----
+    const int off = off0 + k * osy;
+#pragma unroll
+    for (int f = 0; f < kGeoFrames; ++f) {
+      if (t0 + f >= t1) break;
+      const float4 padv = __ldg(fi4 + 5 * f);  // FrameInfo is five float4; the pad colour comes first
+      const float4* fr = (const float4*)(fr0b + f * fbytes);
+      DstT* ob = (DstT*)(ob0b + f * stbytes);
+      asm volatile("" : "+l"(fr));
+      asm volatile("" : "+l"(ob));
+      float r = padv.x, g = padv.y, b = padv.z;
+      if (cls != GEO_FILL) {
+        const float4 v00 = __ldg(fr + o00), v01 = __ldg(fr + o01), v10 = __ldg(fr + o10), v11 = __ldg(fr + o11);
+        r = m * fmaf(padv.x, m, fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00))));
+        g = m * fmaf(padv.y, m, fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00))));
+        b = m * fmaf(padv.z, m, fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00))));
       }
-      if (flags & NEXAR_BLUR) {
-        float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
-        cv[idx] = r;
-        cv[cs * cs + idx] = g;
-        cv[2 * cs * cs + idx] = b;
-        continue;
+      if (tail_fx) {
+        const int frame = frame0 + f;
+        const int idx = y * cs + x;
+        if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+        if (flags & NEXAR_NOISE) {
+          const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
+          r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+          g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
+          b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+        }
+        if (flags & NEXAR_BLUR) {
+          float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+          cv[idx] = r;
+          cv[cs * cs + idx] = g;
+          cv[2 * cs * cs + idx] = b;
+          continue;
+        }
+        point_effects(r, g, b, cp, flags, y, x);
       }
-      point_effects(r, g, b, cp, flags, y, x);
+      // nscale / nbias are 1 / 0 when the output is not normalised
+      store_out_global<DstT>(ob + off, fmaf(r, A.nscale[0], A.nbias[0]));
+      store_out_global<DstT>(ob + (off + osc), fmaf(g, A.nscale[1], A.nbias[1]));
+      store_out_global<DstT>(ob + (off + 2 * osc), fmaf(b, A.nscale[2], A.nbias[2]));
     }
-    DstT* const o = obase + (int64_t)y * A.sy;
-    store_out<DstT>(o, 0, fmaf(r, ns0, nb0));
-    store_out<DstT>(o, A.sc, fmaf(g, ns1, nb1));
-    store_out<DstT>(o, 2 * A.sc, fmaf(b, ns2, nb2));
   }
 }
 
@@ -1733,7 +1768,11 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const int cs = P.cs;
     frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
     colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
-    geometry_kernel<DstT><<<dim3((cs + 31) / 32, (cs + 8 * kGeoRows - 1) / (8 * kGeoRows), nf), 256, 0, st>>>(P, K);
+    const dim3 ggrid((cs + 31) / 32, (cs + 8 * kGeoRows - 1) / (8 * kGeoRows), a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
+    if (a->any_flags & kTailFlags)
+      geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
+    else
+      geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
     g_launches += 3;
     if (blur_mode) {
       blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
@@ -1789,6 +1828,10 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   K.pass = 0;
   // stages no clip of the batch needs are not launched; within a launch, clips without the flag exit at once.
   const int aug_mode = (a->any_flags & NEXAR_AUG) != 0, blur_mode = (a->any_flags & NEXAR_BLUR) != 0;
+  if (aug_mode) {  // K3 addresses one frame of the destination with 32-bit element offsets
+    const double span = 2.0 * std::fabs((double)K.sc) + (double)(p->g.canvas - 1) * (std::fabs((double)K.sy) + std::fabs((double)K.sx));
+    if (span >= 2147483647.0) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: destination strides span more than 2^31 elements per frame");
+  }
   if (p->src_dtype == NEXAR_SRC_U8) {
     if (a->dst_dtype == NEXAR_DST_F32) return launch_all<uint8_t, float>(p, a, K, aug_mode, blur_mode);
     return launch_all<uint8_t, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
