@@ -288,3 +288,36 @@ def test_extreme_parameters_against_oracle():
         want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, params)
         err = float(np.abs(out - want).max())
         assert err <= TOL_AFTER, (k, err)
+
+
+@pytest.mark.parametrize("t", [1, 3, 5, 9])
+def test_frames_of_a_clip_do_not_depend_on_how_they_are_grouped(t):
+    """K3 computes a pixel's geometry once and reuses it for groups of frames of the clip: a T-frame clip must equal
+    its frames transformed one by one with the same parameters, bit for bit, for every group remainder; clips with
+    and without augmentation (and with tail effects) share one batch."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    kw = dict(mode="train", crop_size=64, enable_custom_augmentation=True)
+    tf = _tf(kw)
+    base = dict(brightness=1.05, contrast=0.93, saturation=1.08, hue=0.03, rotation=4.0, scale=0.97, shear=1.5,
+                translate_x=2.0, translate_y=-1.5, apply_affine=True, apply_grayscale=False, apply_noise=False,
+                apply_blur=False, apply_cutout=False, apply_color_inversion=False, apply_solarization=False,
+                apply_posterization=False)
+    recs = [{"flip": False, "aug": dict(base), "crop": None},
+            {"flip": True, "aug": None, "crop": None},
+            {"flip": True, "aug": dict(base, rotation=-11.0, apply_grayscale=True, apply_color_inversion=True), "crop": None},
+            {"flip": False, "aug": dict(base, rotation=0.0, scale=1.0, shear=0.0, translate_x=0.0, translate_y=0.0,
+                                        apply_affine=False), "crop": None}]
+    clips = np.stack([make_clip_np(t, 96, 160, 300 + i, "dashcam") for i in range(len(recs))])
+    frames = torch.from_numpy(clips).cuda()
+    whole = tf.forward_batch(frames, params=recs).float().cpu().numpy()          # [B, 3, T, cs, cs]
+    singles = frames.reshape(len(recs) * t, 1, 96, 160, 3)
+    one = tf.forward_batch(singles, params=[r for r in recs for _ in range(t)]).float().cpu().numpy()
+    one = one.reshape(len(recs), t, 3, 64, 64).transpose(0, 2, 1, 3, 4)
+    assert np.array_equal(whole, one)
+    cfg = O.TransformConfig(mode="train", crop_size=64, enable_custom_augmentation=True, aug=O.AugConfig())
+    for i, r in enumerate(recs):
+        if r["aug"] is None:
+            continue
+        want = O.apply_clip_transform(clips[i].transpose(3, 0, 1, 2), cfg, {"flip": r["flip"], "aug": r["aug"]})
+        err = float(np.abs(whole[i] - want).max())
+        assert err <= TOL_AFTER, (i, err)
