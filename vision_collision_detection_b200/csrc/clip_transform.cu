@@ -791,11 +791,39 @@ __device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
 #define NEXAR_E_BEGIN1 8u
 #define NEXAR_E_ROWSHIFT 4
 
+// ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <int KX, int NT, int MINB, int RS, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[32];
+  __shared__ __align__(8) unsigned long long rowbar;  // "row staged" barrier: one arrival per warp, waited on one pair later
   constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine (multiple of 4)
   const int tid = threadIdx.x;
   const int frame = blockIdx.y;
@@ -877,7 +905,15 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     // the band's control words, staged in shared memory: the loop reads them with a uniform address, one pair ahead
     uint4* const ctl = (uint4*)(wsm + NG * NT);
     for (int e = tid; e <= plast - p0 + 1; e += NT) ctl[e] = __ldg(P.pairs + p0 + e);  // table has a spare entry
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&rowbar);
+    if (tid == 0) {
+      mbar_init(bar, NT / 32);
+      mbar_fence_init();
+    }
     __syncthreads();
+    unsigned phase = 0u;  // parity of the barrier phase the next wait is for
+    int pend = -1;        // output row staged but not yet resampled horizontally (-1: none)
+    unsigned pbuf = 0u;   // its staging buffer
     uint4 e_nx = ctl[0];
     const uint4* tp = ctl + 1;
     if (tid < 32) {
@@ -917,6 +953,49 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
     }                                                                                         \
   }
+// horizontal pass of one staged row (thread = output pixel, three channels)
+#define NEXAR_HORIZ(ROW, BUF)                                                                              \
+  {                                                                                                        \
+    if (hth) {                                                                                         \
+      const unsigned* src = (const unsigned*)(smem_raw + (BUF) + hbyte);                              \
+      /* two taps per step: regroup (R0 G0)(B0 R1)(G1 B1) into per-channel pairs, dp2a against the low and */ \
+      /* the high tap bytes; value * 2^15 * sum(taps) = hi * 256 + lo (< 2^31) */                     \
+      unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
+      uint4 wq = wsm[tid];                                                                             \
+      _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
+        const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
+        const unsigned ww = (m & 3) == 0 ? wq.x : (m & 3) == 1 ? wq.y : (m & 3) == 2 ? wq.z : wq.w;    \
+        const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
+                       bb = __byte_perm(w1, w2, 0x7610);                                               \
+        rl = __dp2a_lo(rr, ww, rl); rh = __dp2a_hi(rr, ww, rh);                                        \
+        gl = __dp2a_lo(gg, ww, gl); gh = __dp2a_hi(gg, ww, gh);                                        \
+        bl_ = __dp2a_lo(bb, ww, bl_); bh = __dp2a_hi(bb, ww, bh);                                      \
+        if ((m & 3) == 3 && (m + 1) / 4 < NG) wq = wsm[((m + 1) / 4) * NT + tid];                      \
+      }                                                                                                \
+      float r = (float)(int)(rh * 256u + rl) * post;                                                   \
+      float g = (float)(int)(gh * 256u + gl) * post;                                                   \
+      float bl = (float)(int)(bh * 256u + bl_) * post;                                                 \
+      const int y = (ROW) + B.oy;                                                                        \
+      if (aug) {                                                                                       \
+        const float bright = cp->brightness;                                                           \
+        r = clamp01(__fmul_rn(bright, r));                                                             \
+        g = clamp01(__fmul_rn(bright, g));                                                             \
+        bl = clamp01(__fmul_rn(bright, bl));                                                           \
+        gsum += gray_of(r, g, bl);                                                                     \
+        ibase[y * A.bw + xo] = make_float4(r, g, bl, 0.0f);                                            \
+      } else {                                                                                         \
+        DstT* const o = obase + ((int64_t)y * A.sy + (int64_t)xo * A.sx);                              \
+        if (A.normalize) {                                                                             \
+          r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
+          g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
+          bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
+        }                                                                                              \
+        store_out<DstT>(o, 0, r);                                                                      \
+        store_out<DstT>(o, A.sc, g);                                                                   \
+        store_out<DstT>(o, 2 * A.sc, bl);                                                              \
+      }                                                                                                \
+    }                                                                                                  \
+  }
 // One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk.  As soon as their bytes have been
 // interleaved into lo/hi the same registers are refilled with pair p+2 (two register sets ping-pong, so
 // every load has almost two iterations to land).
@@ -946,8 +1025,14 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         if (ez & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, ey) else NEXAR_ACCUM(acc1, ey)                 \
       }                                                                                                    \
     }                                                                                                      \
+    if (pend >= 0) { /* the row staged by an earlier pair: by now every warp has arrived, the wait is free */ \
+      mbar_wait(bar, phase);                                                                               \
+      phase ^= 1u;                                                                                         \
+      NEXAR_HORIZ(pend, pbuf)                                                                              \
+      pend = -1;                                                                                           \
+    }                                                                                                      \
     if (ez & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
-      const int row = (int)((ez >> NEXAR_E_ROWSHIFT) & 0xFFFu);                                                      \
+      const int row = (int)((ez >> NEXAR_E_ROWSHIFT) & 0xFFFu);                                            \
       const bool s1 = (ez & NEXAR_E_SLOT) != 0u;                                                          \
       if (row >= i0 && row < i1) {                                                                         \
         if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
@@ -958,46 +1043,10 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
             l2_prefetch_bulk(frame_base + o0, (unsigned)min((int64_t)8 * rs, (int64_t)P.src_h * rs - o0)); \
           }                                                                                                \
         }                                                                                                  \
-        __syncthreads();                                                                                   \
-        if (hth) {                                                                                         \
-          const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
-          /* two taps per step: regroup (R0 G0)(B0 R1)(G1 B1) into per-channel pairs, dp2a against the low and */ \
-          /* the high tap bytes; value * 2^15 * sum(taps) = hi * 256 + lo (< 2^31) */                     \
-          unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
-          uint4 wq = wsm[tid];                                                                             \
-          _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
-            const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
-            const unsigned ww = (m & 3) == 0 ? wq.x : (m & 3) == 1 ? wq.y : (m & 3) == 2 ? wq.z : wq.w;    \
-            const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
-                           bb = __byte_perm(w1, w2, 0x7610);                                               \
-            rl = __dp2a_lo(rr, ww, rl); rh = __dp2a_hi(rr, ww, rh);                                        \
-            gl = __dp2a_lo(gg, ww, gl); gh = __dp2a_hi(gg, ww, gh);                                        \
-            bl_ = __dp2a_lo(bb, ww, bl_); bh = __dp2a_hi(bb, ww, bh);                                      \
-            if ((m & 3) == 3 && (m + 1) / 4 < NG) wq = wsm[((m + 1) / 4) * NT + tid];                      \
-          }                                                                                                \
-          float r = (float)(int)(rh * 256u + rl) * post;                                                   \
-          float g = (float)(int)(gh * 256u + gl) * post;                                                   \
-          float bl = (float)(int)(bh * 256u + bl_) * post;                                                 \
-          const int y = row + B.oy;                                                                        \
-          if (aug) {                                                                                       \
-            const float bright = cp->brightness;                                                           \
-            r = clamp01(__fmul_rn(bright, r));                                                             \
-            g = clamp01(__fmul_rn(bright, g));                                                             \
-            bl = clamp01(__fmul_rn(bright, bl));                                                           \
-            gsum += gray_of(r, g, bl);                                                                     \
-            ibase[y * A.bw + xo] = make_float4(r, g, bl, 0.0f);                                            \
-          } else {                                                                                         \
-            DstT* const o = obase + ((int64_t)y * A.sy + (int64_t)xo * A.sx);                              \
-            if (A.normalize) {                                                                             \
-              r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
-              g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
-              bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
-            }                                                                                              \
-            store_out<DstT>(o, 0, r);                                                                      \
-            store_out<DstT>(o, A.sc, g);                                                                   \
-            store_out<DstT>(o, 2 * A.sc, bl);                                                              \
-          }                                                                                                \
-        }                                                                                                  \
+        __syncwarp();                                                                                      \
+        if ((tid & 31) == 0) mbar_arrive(bar); /* release: this warp's part of the row is staged */        \
+        pend = row;                                                                                        \
+        pbuf = bufoff;                                                                                     \
         bufoff = vbytes - bufoff; /* other staging buffer */                                               \
       }                                                                                                    \
       const unsigned wpost = ez & 0xFFFF0000u;                                                             \
@@ -1013,6 +1062,11 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       NEXAR_PAIR(a1, b1, 6)
       ptr += 4u * rs;
     }
+    if (pend >= 0) {
+      mbar_wait(bar, phase);
+      NEXAR_HORIZ(pend, pbuf)
+    }
+#undef NEXAR_HORIZ
 #undef NEXAR_PAIR
 #undef NEXAR_ACCUM
 #undef NEXAR_ACCUM_BEGIN
@@ -1028,33 +1082,6 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const float s = block_sum(gsum, red);
     if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
-}
-
-// ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0u;
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-               :: "r"(bar), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // K1 (TMA variant): same arithmetic as resize_fast_kernel, but the source rows arrive through an
