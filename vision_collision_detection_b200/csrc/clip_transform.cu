@@ -734,22 +734,24 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 
 
 // ---------------------------------------------------------------------------------
-// K1 (fast variant): input-stationary fixed-point vertical pass + fp32 horizontal pass.
+// K1 (fast variant): input-stationary fixed-point vertical pass + fixed-point horizontal pass, both on dp2a.
 //
 // Down-scaling (>= 2x vertically) uint8 frames whose rows are a multiple of 16 bytes.  A CTA owns
 // one band of resized rows of one frame and streams the source rows it needs exactly once, two rows
-// per step.  Every thread keeps one 16-byte column chunk: 128-bit coalesced streaming loads, one
-// pair ahead in registers (ping-pong), while warp 0 pushes the rows LOOKAHEAD pairs ahead into L2
-// through the bulk-copy engine (cp.async.bulk.prefetch.L2).  The two rows' bytes are interleaved
-// with PRMT and fed to dp2a against the 16-bit fixed-point taps of the (at most two) output rows
-// alive at that height.  The per-pair control words (taps, begin/flush flags) are read one pair
-// ahead, so no branch waits on its own load.  A finished row is rounded to 15-bit fixed point (value*128),
-// staged in shared memory (double buffered: one __syncthreads per output row) and resampled
-// horizontally in fp32, one output pixel per thread with its taps in registers.  The uint16 ->
-// float conversion is a single PRMT that builds the float 2^15 + v; the constant 2^15 * sum(w) is
-// removed after the tap loop.  Error of the fixed-point steps against an exact evaluation (720p -> 224
-// noise): max 2.2e-5 of full scale, dominated by the 2^-8 staging rounding (bound: weights 2^-16 * 255 *
-// taps/2 + staging 2^-8 in 0..255 units < 1.2e-4 of full scale; gate: 1/255 before, 1e-3 after normalisation).
+// per step.  Every thread keeps one 16-byte column chunk: 128-bit coalesced streaming loads through a running
+// pointer ([pointer + immediate] when the row stride is a compile-time constant), two pairs ahead in registers
+// (ping-pong), while thread 0 pushes the rows LOOKAHEAD pairs ahead into L2 through the bulk-copy engine
+// (cp.async.bulk.prefetch.L2).  The two rows' bytes are interleaved with PRMT and fed to dp2a against the
+// 15-bit fixed-point taps of the (at most two) output rows alive at that height.  The per-pair control words
+// (taps, begin/flush flags) sit in shared memory and are read one pair ahead with a uniform address, so no
+// branch waits on its own load.  A finished row is rounded to 15-bit fixed point (value * 128) and staged in
+// shared memory (double buffered); every warp then arrives on an mbarrier and goes on with the NEXT row pair,
+// and only after that waits (by then for free) and resamples the staged row horizontally, one output pixel per
+// thread: the staged (R0 G0)(B0 R1)(G1 B1) words are regrouped per channel with PRMT and dp2a'd against the
+// horizontal taps, which are 15-bit too and stored as byte pairs (low bytes | high bytes, see build_fast_tables):
+// value * 2^15 * sum(taps) = hi * 256 + lo.  Error of the fixed-point steps against an exact evaluation (720p -> 224
+// noise): max < 3e-5 of full scale (bound: 2 x weights 2^-16 * 255 * taps/2 + staging 2^-8 in 0..255 units;
+// gate: 1/255 before, 1e-3 after normalisation).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ float magic_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4105)); }
 __device__ __forceinline__ float magic_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x47u, 0x4325)); }
@@ -1414,7 +1416,9 @@ constexpr int kColourPerThread = 4;
 #define NEXAR_COL_MINB 6
 #endif
 __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
-  const int frame = blockIdx.y;
+  // K1 wrote the frames in ascending order, so the LAST ones are still in L2: walk them in descending order (and
+  // K3 then starts with frame 0, which this kernel wrote last)
+  const int frame = (int)(gridDim.y - 1u - blockIdx.y);
   const float4* fi4 = (const float4*)(A.finfo + frame);
   const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, hue, -
   if (!(__float_as_uint(q3.z) & NEXAR_AUG)) return;
