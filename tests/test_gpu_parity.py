@@ -321,3 +321,36 @@ def test_frames_of_a_clip_do_not_depend_on_how_they_are_grouped(t):
         want = O.apply_clip_transform(clips[i].transpose(3, 0, 1, 2), cfg, {"flip": r["flip"], "aug": r["aug"]})
         err = float(np.abs(whole[i] - want).max())
         assert err <= TOL_AFTER, (i, err)
+
+
+@pytest.mark.parametrize("h,w,cs,pad", [(720, 1280, 224, 64), (96, 160, 56, 16), (97, 131, 64, 7)])
+def test_padded_source_rows_equal_packed_rows(h, w, cs, pad):
+    """Decoders hand out frames whose rows are padded: the C ABI takes the row stride in bytes.  A padded 720p
+    source takes the run-time-stride instantiation of the fast kernel (the packed one is specialised on 3840 bytes),
+    odd strides take the general kernel; all must equal the packed result bit for bit."""
+    from vision_collision_detection_b200.engine import get_engine, _alloc_out
+    from vision_collision_detection_b200.params import pack_clip_params
+    from vision_collision_detection_b200.synth import make_clip_np
+    t = 3
+    clip = make_clip_np(t, h, w, 77, "dashcam")
+    tf = _tf(dict(mode="train", crop_size=cs, enable_custom_augmentation=True))
+    random.seed(5)
+    frames = torch.from_numpy(clip).cuda().unsqueeze(0)
+    want = tf.forward_batch(frames).float().cpu().numpy()
+    params = tf.last_params
+    eng = get_engine(frames.device)
+    plan = tf._plan(eng, h, w, torch.uint8)
+    stride = w * 3 + pad
+    buf = torch.full((t, h, stride), 255, dtype=torch.uint8, device="cuda")       # the padding must never be read
+    buf[:, :, :w * 3] = frames[0].reshape(t, h, w * 3)
+    offsets = torch.arange(t, dtype=torch.int64, device="cuda") * (h * stride)
+    packed, any_flags = pack_clip_params(params, cs, tf.video_aug)
+    out, strides = _alloc_out("BCTHW", 1, t, cs, torch.float32, frames.device)
+    eng.run(plan, buf, offsets, 1, t, eng.upload_params(packed), any_flags, out, strides,
+            tf.normalize, tf.video_mean, tf.video_std, src_row_stride=stride)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    if (w * 3) % 16 == 0 and stride % 16 == 0:
+        assert np.array_equal(got, want)            # same kernel arithmetic, different addressing
+    else:
+        assert np.abs(got - want).max() <= 2.5e-4    # general kernel (fp32) against the fast kernel or itself
