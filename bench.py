@@ -30,6 +30,7 @@ WORKLOADS = {
     "cfg2": (32, 16, 720, 1280, 224),
     "cfg3": (32, 32, 720, 1280, 320),
     "tiny": (4, 4, 180, 320, 112),
+    "cfg2s": (8, 16, 720, 1280, 224),   # a trainer-sized batch (cfg5 uses 8 clips per GPU): band-count tuning
     # BASELINE configs[3]: one 40 s x 30 fps 720p video, val chain, every frame transformed once,
     # 16-frame windows at stride 8 as strided views (149 windows); "clips" = windows
     "cfg4": (1, 1200, 720, 1280, 224),

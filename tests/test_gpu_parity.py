@@ -354,3 +354,22 @@ def test_padded_source_rows_equal_packed_rows(h, w, cs, pad):
         assert np.array_equal(got, want)            # same kernel arithmetic, different addressing
     else:
         assert np.abs(got - want).max() <= 2.5e-4    # general kernel (fp32) against the fast kernel or itself
+
+
+@pytest.mark.parametrize("name", ["custom_720p_dashcam", "custom_small_s0", "ncwv_small_s2"])
+def test_result_does_not_depend_on_the_band_count(name):
+    """The resize kernel splits a frame into bands of rows (the count follows the batch size); the frame's gray mean
+    (contrast blend) is summed in fixed point, so augmented results are bit-identical for any banding - a clip's
+    output does not depend on the batch it travels in."""
+    from vision_collision_detection_b200 import _lib
+    c = load_case(name)
+    L = _lib.lib()
+    outs = []
+    try:
+        for bands in (1, 2, 5, 8):
+            L.nexar_set_fast_bands(bands)
+            outs.append(_run(_tf(c["kwargs"]), c["clip"], c["params"]))
+    finally:
+        L.nexar_set_fast_bands(0)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])

@@ -420,7 +420,7 @@ static_assert(sizeof(FrameInfo) == 80, "FrameInfo is five 16-byte words");
 
 struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
-  float* gray_partial;  // [2][n_frames][kMaxBands]
+  unsigned long long* gray_partial;  // [2][n_frames][kMaxBands] fixed-point (2^-22) gray sums: exact, order-independent
   FrameInfo* finfo;     // [n_frames] per-frame constants for K2/K3, written by K1.5
   float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
@@ -435,8 +435,8 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base, unsig
   char* b = (char*)base;
   w.clip_max = (unsigned*)(b + off);
   off = align_up(off + (size_t)n_clips * sizeof(unsigned), 256);
-  w.gray_partial = (float*)(b + off);
-  off = align_up(off + 2 * nf * kMaxBands * sizeof(float), 256);
+  w.gray_partial = (unsigned long long*)(b + off);
+  off = align_up(off + 2 * nf * kMaxBands * sizeof(unsigned long long), 256);
   w.finfo = (FrameInfo*)(b + off);
   off = align_up(off + nf * sizeof(FrameInfo), 256);
   w.inter = (float4*)(b + off);  // only augmented clips use it
@@ -470,7 +470,7 @@ struct KArgs {
   int normalize;
   float nscale[3], nbias[3];  // out = v * nscale + nbias  ((v - mean) / std)
   unsigned* clip_max;
-  float* gray_partial;
+  unsigned long long* gray_partial;
   FrameInfo* finfo;
   float4* inter;
   float* canvas;
@@ -513,16 +513,20 @@ __device__ __forceinline__ void store_out_global<__nv_bfloat16>(__nv_bfloat16* p
   asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(h) : "memory");
 }
 
-__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+// The frame's gray mean (torchvision's contrast blend) is accumulated in 2^-22 fixed point: integer sums are exact,
+// so the mean does not depend on the band count, the thread mapping or which resize kernel produced the pixels.
+constexpr float kGrayFix = 4194304.0f;  // 2^22: a thread sums <= 1023 pixels in 32 bits
+__device__ __forceinline__ unsigned gray_fix(float r, float g, float b) { return __float2uint_rn(gray_of(r, g, b) * kGrayFix); }
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* red /*[32]*/) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __syncthreads();
   if (lane == 0) red[wid] = v;
   __syncthreads();
   const int nw = (blockDim.x + 31) >> 5;
-  float t = 0.0f;
+  unsigned long long t = 0ull;
   if (wid == 0) {
-    t = lane < nw ? red[lane] : 0.0f;
+    t = lane < nw ? red[lane] : 0ull;
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   }
   return t;  // valid in warp 0
@@ -629,7 +633,7 @@ __global__ void clip_max_kernel(DevPlan P, KArgs A) {
 template <typename SrcT, typename DstT>
 __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A) {
   extern __shared__ float vbuf[];  // [src_w*3] vertical-pass result of the current resized row
-  __shared__ float red[32];
+  __shared__ unsigned long long red[32];
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
   const int t = frame - clip * A.T;
@@ -658,7 +662,8 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
     nbi[c] = A.normalize ? A.nbias[c] : 0.0f;
   }
   const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
-  float vmax = -INFINITY, gsum = 0.0f;
+  float vmax = -INFINITY;
+  unsigned long long gsum = 0ull;  // one thread may cover many pixels here
 
   for (int i = i0; i < i1; ++i) {
     const int ys = P.ystart[i], yc = P.ycount[i];
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
         r = clamp01(__fmul_rn(bright, r));
         g = clamp01(__fmul_rn(bright, g));
         b = clamp01(__fmul_rn(bright, b));
-        gsum += gray_of(r, g, b);
+        gsum += gray_fix(r, g, b);
         A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (x - B.bx0)] = make_float4(r, g, b, 0.0f);
       } else {
         const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
     if ((threadIdx.x & 31) == 0 && vmax > 1.0f) atomicOr(&A.clip_max[clip], 1u);
   }
   if (aug) {
-    const float s = block_sum(gsum, red);
+    const unsigned long long s = block_sum(gsum, red);
     if (threadIdx.x == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
 }
@@ -824,7 +829,7 @@ template <int KX, int NT, int MINB, int RS, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[32];
+  __shared__ unsigned long long red[32];
   __shared__ __align__(8) unsigned long long rowbar;  // "row staged" barrier: one arrival per warp, waited on one pair later
   constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine (multiple of 4)
   const int tid = threadIdx.x;
@@ -853,7 +858,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
 
   const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
-  float gsum = 0.0f;
+  unsigned gsum = 0u;
   unsigned orv = 0u;
 
   if (i0 < i1) {
@@ -983,7 +988,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         r = clamp01(__fmul_rn(bright, r));                                                             \
         g = clamp01(__fmul_rn(bright, g));                                                             \
         bl = clamp01(__fmul_rn(bright, bl));                                                           \
-        gsum += gray_of(r, g, bl);                                                                     \
+        gsum += gray_fix(r, g, bl);                                                                     \
         ibase[y * A.bw + xo] = make_float4(r, g, bl, 0.0f);                                            \
       } else {                                                                                         \
         DstT* const o = obase + ((int64_t)y * A.sy + (int64_t)xo * A.sx);                              \
@@ -1081,7 +1086,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
   }
   if (aug) {
-    const float s = block_sum(gsum, red);
+    const unsigned long long s = block_sum((unsigned long long)gsum, red);
     if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
 }
@@ -1094,7 +1099,7 @@ template <int KX, int NT, int MINB, int NS, typename DstT>
 __global__ void __launch_bounds__(NT, MINB)
 resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[32];
+  __shared__ unsigned long long red[32];
     const int tid = threadIdx.x;
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
@@ -1121,7 +1126,7 @@ resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KAr
   for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
 
   const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
-  float gsum = 0.0f;
+  unsigned gsum = 0u;
   unsigned orv = 0u;
 
   if (i0 < i1) {
@@ -1279,7 +1284,7 @@ resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KAr
             r = clamp01(__fmul_rn(bright, r));                                                             \
             g = clamp01(__fmul_rn(bright, g));                                                             \
             bl = clamp01(__fmul_rn(bright, bl));                                                           \
-            gsum += gray_of(r, g, bl);                                                                     \
+            gsum += gray_fix(r, g, bl);                                                                     \
             ((float4*)optr)[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                              \
           } else {                                                                                         \
             DstT* const o = (DstT*)optr + (int64_t)y * A.sy;                                               \
@@ -1315,7 +1320,7 @@ resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KAr
     if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
   }
   if (aug) {
-    const float s = block_sum(gsum, red);
+    const unsigned long long s = block_sum((unsigned long long)gsum, red);
     if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
 }
@@ -1369,10 +1374,10 @@ __device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const
 }
 
 __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, int frame, int slot, int nbands) {
-  const float* gp = A.gray_partial + ((size_t)slot * A.n_frames + frame) * kMaxBands;
-  float s = 0.0f;
+  const unsigned long long* gp = A.gray_partial + ((size_t)slot * A.n_frames + frame) * kMaxBands;
+  unsigned long long s = 0ull;
   for (int b = 0; b < nbands; ++b) s += gp[b];
-  return s / (float)(P.cs * P.cs);
+  return (float)((double)s / ((double)kGrayFix * (double)(P.cs * P.cs)));
 }
 
 // K1.5: one thread per frame.  Reduces the band partial sums to the frame's gray mean (fixed order:
@@ -1697,6 +1702,17 @@ __global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
 // ---------------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------------
+static int sm_count() {  // of the current device (cached per device)
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 template <typename SrcT, typename DstT>
 static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K, int aug_mode, int blur_mode) {
   cudaStream_t st = (cudaStream_t)a->stream;
@@ -1711,9 +1727,17 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
                         a->src_row_stride % 16 == 0 && ((uintptr_t)a->src % 16) == 0;
   if (use_fast) {
-    nbands = g_fast_bands > 0 ? imin(g_fast_bands, kMaxBands) : imax(1, imin(kMaxBands, (vis_rows + 24) / 25));
-    nbands = imax(1, imin(nbands, vis_rows));
     const int need_threads = imax(P.src_w * 3 / 16, imin(P.rw, P.cs));
+    // Bands per frame: every band re-reads the source rows it shares with its neighbour and pays the CTA prologue, so
+    // fewer is better as long as the grid still fills the machine about 4.5 times over (measured on cfg2 / cfg3 /
+    // 8-clip batches: 4 / 2 / 8 bands beat the old fixed 25-rows-per-band rule by 1-6 %).
+    if (g_fast_bands > 0) {
+      nbands = imin(g_fast_bands, kMaxBands);
+    } else {
+      const int slots = sm_count() * (need_threads <= 256 ? NEXAR_MINB : 2);
+      nbands = imin(8, ((9 * slots) / 2 + nf - 1) / nf);
+    }
+    nbands = imax(1, imin(nbands, imin(kMaxBands, vis_rows)));
     const int kx = P.kx_al;
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
