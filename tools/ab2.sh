@@ -8,4 +8,4 @@ for lib in "$@"; do
     NEXAR_LIB=$PWD/$lib timeout 120 python bench.py --workload ${WORKLOAD:-cfg2} --mode $mode --no-cpu-baseline --no-e2e > gpurun_out/ab_${n}_${mode}.log 2>&1
   done
 done
-NEXAR_LIB=$PWD/${@: -1} timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo pytest=$? >> gpurun_out/pytest.log
+[ -n "$NOTEST" ] || NEXAR_LIB=$PWD/${@: -1} timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo pytest=$? >> gpurun_out/pytest.log
