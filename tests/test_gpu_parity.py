@@ -373,3 +373,22 @@ def test_result_does_not_depend_on_the_band_count(name):
         L.nexar_set_fast_bands(0)
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])
+
+
+@pytest.mark.parametrize("h,w,cs", [(720, 1280, 320), (720, 1280, 448), (360, 640, 288)])
+def test_wide_outputs_with_augmentation_against_oracle(h, w, cs):
+    """Outputs wider than the 256-thread block of the resize kernel (two pixels per thread in the horizontal pass;
+    BASELINE config 3 is 720p -> 320) with the live call site's augmentation, two frames, against the oracle."""
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = make_clip_np(2, h, w, 500 + cs, "dashcam")
+    kw = dict(mode="train", crop_size=cs, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = _tf(kw)
+    random.seed(cs)
+    params = tf.sample_params(1, h, w)[0]
+    out = _run(tf, clip, params)
+    cfg = O.TransformConfig(mode="train", crop_size=cs, enable_custom_augmentation=True, aug=O.AugConfig(
+        brightness_range=(0.9, 1.1), contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5)))
+    want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": params["flip"], "aug": params["aug"]})
+    err = float(np.abs(out - want).max())
+    assert err <= TOL_AFTER, err
