@@ -275,8 +275,16 @@ def main():
 
     # ---- device-resident timing ("value") ------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.2 s to stream
-    for i in range(args.warmup):
-        step(i)
+    # warm-up: the W steps asked for, and at least 10 steps / 50 ms so that the clocks have ramped and the one-time
+    # costs (plan tables, workspace, pinned parameter ring) are behind us even when W is tiny; "warmup" reports the count
+    t_w = time.time()
+    n_warm = 0
+    while n_warm < max(args.warmup, 10) or (time.time() - t_w < 0.05 and n_warm < 1000):
+        step(n_warm)
+        n_warm += 1
+        if n_warm % 8 == 0:
+            torch.cuda.synchronize()
+    args.warmup = n_warm
     barrier()
     from vision_collision_detection_b200 import _lib
     _lib.lib().nexar_profile_begin(args.steps + 8)
