@@ -173,6 +173,79 @@ def test_deferred_dataset_and_collate_without_cuda():
     assert list(V.shard_clips(10, 1, 4)) == [3, 4, 5] and list(V.shard_clips(10, 3, 4)) == [9]
 
 
+def test_sensor_sync_is_bit_exact_with_the_reference_pandas_expression():
+    """SURVEY F4 (nexar_videos.py:318-341): numpy.interp on the valid samples == reindex/union/interpolate('index')."""
+    from oracle.sensor_oracle import sync_sensor_pandas
+    from vision_collision_detection_b200.sensors import sync_sensor_to_frames
+    rng = np.random.default_rng(0)
+    checked = 0
+    for trial in range(24):
+        n = int(rng.integers(2, 300))
+        fps = float(rng.choice([30.0, 29.97, 25.0, 10.0, 59.94]))
+        fc = int(rng.integers(1, 900))
+        t = 1.7e9 + np.cumsum(rng.uniform(0.005, 0.02, n))
+        a = rng.normal(size=(n, 4))
+        if trial % 5 == 0:
+            a[rng.integers(0, n, 3), rng.integers(0, 4, 3)] = np.nan      # holes are interpolated over
+        if trial % 7 == 0:
+            a[0, 1] = np.nan                                              # a leading hole stays NaN
+        if trial % 3 == 0:                                                # samples exactly on frame times
+            k = min(n - 1, 5)
+            t[1:1 + k] = t[0] + np.arange(1, 1 + k) / fps
+            t = np.sort(t)
+            if (np.diff(t) == 0).any():
+                continue
+        if trial % 4 == 0:                                                # unsorted file order
+            perm = rng.permutation(n)
+            perm = np.concatenate([[0], perm[perm != 0]])                 # the first row defines time zero
+            t, a = t[perm], a[perm]
+        got = sync_sensor_to_frames(t, a, fc, fps)
+        want = sync_sensor_pandas(t, a, fc, fps)
+        assert got.dtype == np.float64 and np.array_equal(got, want, equal_nan=True), trial
+        checked += 1
+    assert checked >= 16
+    with pytest.raises(ValueError):                                       # pandas: cannot reindex on duplicate labels
+        sync_sensor_to_frames(np.array([5.0, 5.5, 5.5]), np.zeros((3, 4)), 10, 30.0)
+
+
+def test_dataset_sensor_window_follows_the_reference(tmp_path):
+    """nexar_videos.py:453-477: rows [start, end) of the synced table, last row repeated, zeros without a CSV."""
+    from oracle.sensor_oracle import sync_sensor_pandas
+    from vision_collision_detection_b200 import sensors as SN
+    rng = np.random.default_rng(3)
+    n_frames, vfps = 80, 20.0
+    t = 100.0 + np.cumsum(rng.uniform(0.004, 0.012, 700))
+    a = rng.normal(size=(700, 4))
+    for vid in ("with_csv", "no_csv", "short"):
+        os.makedirs(tmp_path / vid / "signals", exist_ok=True)
+        (tmp_path / vid / f"{vid}.mp4").write_bytes(b"")
+    with open(tmp_path / "with_csv" / "signals" / SN.SENSOR_FILE, "w") as f:
+        f.write(",time_sec,accel_x_G,accel_y_G,accel_z_G,accel_total_G\n")
+        for i in range(len(t)):
+            f.write(",".join([str(i)] + [repr(float(v)) for v in (t[i], *a[i])]) + "\n")
+    with open(tmp_path / "short" / "signals" / SN.SENSOR_FILE, "w") as f:
+        f.write(",time_sec,accel_x_G,accel_y_G,accel_z_G,accel_total_G\n0,1.0,0.1,0.2,0.3,0.4\n1,1.5,0.2,0.3,0.4,0.5\n")
+
+    class Reader(_FakeReader):
+        def get_avg_fps(self):
+            return vfps
+
+    rows = [{"id": v, "video_type": "Normal"} for v in ("with_csv", "no_csv", "short")]
+    ds = V.GpuDashcamDataset(rows, [str(tmp_path)], fps=10, duration=5, transform=None, sample_strategy="center",
+                             decoder=lambda p: Reader(30 if "short" in p else n_frames), defer=True)
+    assert ds.sensor_paths[0].endswith(SN.SENSOR_FILE) and ds.sensor_paths[1] is None
+    full = sync_sensor_pandas(t, a, n_frames, vfps)
+    start = S.start_frame(n_frames, 50, "center")
+    want = full[start:start + 50].astype(np.float32)
+    got = ds[0]["sensor"]
+    assert got.dtype == torch.float32 and tuple(got.shape) == (50, 4)
+    assert np.array_equal(got.numpy(), want)
+    assert float(ds[1]["sensor"].abs().max()) == 0.0                      # no CSV beside the video
+    s = ds[2]["sensor"].numpy()                                           # 30-frame video, window 0..30: last row repeated
+    tab = sync_sensor_pandas(np.array([1.0, 1.5]), np.array([[0.1, 0.2, 0.3, 0.4], [0.2, 0.3, 0.4, 0.5]]), 30, vfps)
+    assert np.array_equal(s[:30], tab.astype(np.float32)) and np.array_equal(s[30:], np.repeat(s[29:30], 20, axis=0))
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "vision_collision_detection_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -28,6 +28,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from .sensors import find_sensor_path, load_and_sync_sensor, window_sensor
 from .video_aug import GpuVideoTransform
 
 
@@ -100,13 +101,16 @@ class GpuDashcamDataset(Dataset):
     """``NvidiaDashcamDataset(metadata_df, base_dirs, fps, duration, is_train, skip_missing, transform,
     sample_strategy, sensor_subdir, time_column)`` work-alike for the frames path.  ``metadata_df`` may be a
     pandas DataFrame or a list of dicts with 'id', 'video_type' and, optionally, 'path' / the time column.
-    IMU/sensor sync is out of scope: 'sensor' is the reference's zero fallback."""
+    'sensor' is the accelerometer CSV interpolated at the frame times and cut to the clip's window
+    (``sensors.py``; nexar_videos.py:301-346, 453-477), zeros when there is no CSV beside the video - pass
+    ``sensor_resolver`` to find it somewhere else."""
 
     def __init__(self, metadata_df, base_dirs=None, fps=10, duration=5, is_train=True, skip_missing=True,
                  transform: Optional[GpuVideoTransform] = None, sample_strategy="random", sensor_subdir="signals",
                  time_column=None, *, decoder: Optional[Callable[[str], Any]] = None,
                  path_resolver: Optional[Callable[[str], Optional[str]]] = None, defer: bool = False,
-                 video_fps_lookup: Optional[Callable[[str], float]] = None):
+                 video_fps_lookup: Optional[Callable[[str], float]] = None,
+                 sensor_resolver: Optional[Callable[[str], Optional[str]]] = None):
         rows = metadata_df.to_dict("records") if hasattr(metadata_df, "to_dict") else list(metadata_df)
         self.fps, self.duration, self.is_train = fps, duration, is_train
         self.transform = transform
@@ -119,7 +123,8 @@ class GpuDashcamDataset(Dataset):
         self.defer = defer
         self.video_fps_lookup = video_fps_lookup
         import os
-        self.rows, self.video_paths = [], []
+        self.sensor_subdir = sensor_subdir
+        self.rows, self.video_paths, self.sensor_paths = [], [], []
         for row in rows:
             path = row.get("path")
             if path is None and path_resolver is not None:
@@ -136,19 +141,36 @@ class GpuDashcamDataset(Dataset):
                 continue
             self.rows.append(row)
             self.video_paths.append(path)
+            self.sensor_paths.append(sensor_resolver(path) if sensor_resolver is not None
+                                     else find_sensor_path(path, sensor_subdir))
 
     def __len__(self):
         return len(self.video_paths)
 
-    def _window(self, reader, row, idx) -> List[int]:
+    def _video_fps(self, reader, idx) -> float:
+        if self.video_fps_lookup:
+            return float(self.video_fps_lookup(self.video_paths[idx]))
+        get = getattr(reader, "get_avg_fps", None)
+        return float(get()) if get is not None else 30.0
+
+    def _window(self, reader, row, idx):
+        """-> (frame indices, start, end) of nexar_videos.py:364-435."""
         n = len(reader)
         need = self.fps * self.duration
         ts, vfps = None, 0.0
         if self.sample_strategy == "metadata_time":
             ts = row.get(self.time_column)
-            vfps = self.video_fps_lookup(self.video_paths[idx]) if self.video_fps_lookup else 30.0
+            vfps = self._video_fps(reader, idx)
         start = select_start_frame(n, need, self.sample_strategy, random, ts, vfps)
-        return window_indices(n, need, start)
+        return window_indices(n, need, start), start, min(start + need, n)
+
+    def _sensor(self, reader, idx, start, end) -> torch.Tensor:
+        """nexar_videos.py:453-477 (frame count / fps come from the decoder instead of a second cv2 open)."""
+        need = self.fps * self.duration
+        n = len(reader)
+        table = load_and_sync_sensor(self.sensor_paths[idx], n, self._video_fps(reader, idx), need) \
+            if self.sensor_paths[idx] else np.zeros((need, 4), np.float32)
+        return torch.from_numpy(window_sensor(table, n, start, end, need)).float()
 
     def __getitem__(self, idx):
         row = self.rows[idx]
@@ -156,7 +178,7 @@ class GpuDashcamDataset(Dataset):
         target, vid = row.get("video_type"), row.get("id")
         try:
             reader = self.decoder(self.video_paths[idx])
-            indices = self._window(reader, row, idx)
+            indices, start, end = self._window(reader, row, idx)
             frames = _to_uint8_array(reader.get_batch(indices))
             if len(frames) < need:          # nexar_videos.py:429-433
                 last = frames[-1] if len(frames) else np.zeros(frames.shape[1:] or (720, 1280, 3), np.uint8)
@@ -165,10 +187,13 @@ class GpuDashcamDataset(Dataset):
             if self.defer:
                 t = self.transform
                 params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
-                return {"frames_u8": frames, "params": params, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+                return {"frames_u8": frames, "params": params, "sensor": self._sensor(reader, idx, start, end),
+                        "target": target, "id": vid}
             video = frames.permute(3, 0, 1, 2)                  # nexar_videos.py:441
             video = self.transform(video) if self.transform else video.float() / 255.0
             frames = video.permute(1, 2, 3, 0)                  # nexar_videos.py:451
+            sensor = self._sensor(reader, idx, start, end)
+            return {"frames": frames, "sensor": sensor, "target": target, "id": vid}
         except Exception:
             # nexar_videos.py:479-489: swallow everything, return an all-zeros clip of the standard size
             size = (224, 224) if self.transform else (720, 1280)
