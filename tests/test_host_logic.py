@@ -246,6 +246,46 @@ def test_dataset_sensor_window_follows_the_reference(tmp_path):
     assert np.array_equal(s[:30], tab.astype(np.float32)) and np.array_equal(s[30:], np.repeat(s[29:30], 20, axis=0))
 
 
+def test_video_dataset_mirror_follows_complete_with_validation():
+    """nexar_complete_with_validation.py:57-234: explicit lists, 'metadata_center' windows, no sensor stream."""
+    paths, labels, ids = ["a.mp4", "b.mp4", "c.mp4", "missing.mp4"], [0, 2, 1, 0], ["a", "b", "c", "m"]
+    meta = [{"id": "a", "t_event": 3.0}, {"id": "b", "t_event": float("nan")}, {"id": "c", "t_event": 100.0}]
+
+    class Reader(_FakeReader):
+        def get_avg_fps(self):
+            return 20.0
+
+    def decoder(path):
+        if "missing" in path:
+            raise IOError("no such video")
+        return Reader(120)
+
+    with pytest.raises(AssertionError):
+        V.GpuVideoDataset(paths, labels[:2])
+    with pytest.raises(AssertionError):
+        V.GpuVideoDataset(paths, labels, sample_strategy="metadata_center")        # needs metadata_df + column
+    ds = V.GpuVideoDataset(paths, labels, ids, fps=10, duration=5, transform=None, sample_strategy="metadata_center",
+                           center_time_column="t_event", metadata_df=meta, decoder=decoder, defer=True)
+    ref = Reader(120).frames
+    a = ds[0]                                                    # centre frame int(3.0 * 20) = 60 -> start 35
+    assert sorted(a) == ["frames_u8", "id", "need", "params", "target"] and a["target"] == 0 and a["id"] == "a"
+    assert torch.equal(a["frames_u8"][0], torch.from_numpy(ref[S.start_frame(120, 50, "metadata_center", random, 3.0, 20.0)]))
+    assert S.start_frame(120, 50, "metadata_center", random, 3.0, 20.0) == 35
+    random.seed(11)
+    want = S.start_frame(120, 50, "metadata_center", random, None, 20.0)          # NaN centre time: random window
+    random.seed(11)
+    assert torch.equal(ds[1]["frames_u8"][0], torch.from_numpy(ref[want]))
+    assert torch.equal(ds[2]["frames_u8"][0], torch.from_numpy(ref[70]))           # past the end: last full window
+    assert ds[3]["frames_u8"] is None
+    batch = V.deferred_collate([ds[0], ds[2], ds[3]])
+    assert "sensor" not in batch and batch["valid"] == [True, True, False] and batch["need"] == 50
+    plain = V.GpuVideoDataset(paths, labels, ids, sample_strategy="center", decoder=decoder)
+    item = plain[0]
+    assert sorted(item) == ["frames", "id", "target"] and tuple(item["frames"].shape) == (50, 48, 64, 3)
+    assert float(item["frames"].max()) <= 1.0                     # no transform: frames / 255 (ncwv:178)
+    assert tuple(plain[3]["frames"].shape) == (50, 720, 1280, 3)  # failure without a transform (ncwv:189-190)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "vision_collision_detection_b200")
     for dirpath, _, files in os.walk(pkg):

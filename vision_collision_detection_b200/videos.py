@@ -188,7 +188,7 @@ class GpuDashcamDataset(Dataset):
                 t = self.transform
                 params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
                 return {"frames_u8": frames, "params": params, "sensor": self._sensor(reader, idx, start, end),
-                        "target": target, "id": vid}
+                        "target": target, "id": vid, "need": need}
             video = frames.permute(3, 0, 1, 2)                  # nexar_videos.py:441
             video = self.transform(video) if self.transform else video.float() / 255.0
             frames = video.permute(1, 2, 3, 0)                  # nexar_videos.py:451
@@ -198,23 +198,109 @@ class GpuDashcamDataset(Dataset):
             # nexar_videos.py:479-489: swallow everything, return an all-zeros clip of the standard size
             size = (224, 224) if self.transform else (720, 1280)
             if self.defer:
-                return {"frames_u8": None, "params": None, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+                return {"frames_u8": None, "params": None, "sensor": torch.zeros(need, 4), "target": target, "id": vid,
+                        "need": need}
             frames = torch.zeros(need, size[0], size[1], 3)
         return {"frames": frames, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
 
 
+class GpuVideoDataset(Dataset):
+    """``VideoDataset(video_paths, labels, video_ids, fps, duration, is_train, transform, sample_strategy,
+    center_time_column, metadata_df)`` work-alike (nexar_complete_with_validation.py:57-234): explicit path / label
+    lists, strategies 'random', 'center' and 'metadata_center' (window centred on ``metadata_df[center_time_column]``
+    seconds, random window when the value is missing), items ``{'frames', 'target', 'id'}`` - no sensor stream.
+    ``defer=True`` returns the uint8 window plus the clip's parameter record for ``GpuAugLoader``."""
+
+    def __init__(self, video_paths, labels, video_ids=None, fps=10, duration=5, is_train=True,
+                 transform: Optional[GpuVideoTransform] = None, sample_strategy="metadata_center",
+                 center_time_column=None, metadata_df=None, *, decoder: Optional[Callable[[str], Any]] = None,
+                 defer: bool = False, video_fps_lookup: Optional[Callable[[str], float]] = None):
+        assert len(video_paths) == len(labels), "video_paths and labels must have same length"      # ncwv:94
+        assert sample_strategy in ("random", "center", "metadata_center"), \
+            "sample_strategy must be 'random', 'center', or 'metadata_center'"                       # ncwv:95-96
+        self.video_paths, self.labels = list(video_paths), list(labels)
+        self.video_ids = list(video_ids) if video_ids is not None else list(range(len(self.video_paths)))
+        self.fps, self.duration, self.is_train = fps, duration, is_train
+        self.transform, self.sample_strategy = transform, sample_strategy
+        self.center_time_column = center_time_column
+        self.decoder = decoder or _decord_reader
+        self.defer = defer
+        self.video_fps_lookup = video_fps_lookup
+        self._center_time: Dict[Any, Any] = {}
+        if sample_strategy == "metadata_center":
+            assert metadata_df is not None, "metadata_df required for 'metadata_center' strategy"  # ncwv:99
+            assert center_time_column is not None, "center_time_column required for 'metadata_center' strategy"
+            rows = metadata_df.to_dict("records") if hasattr(metadata_df, "to_dict") else list(metadata_df)
+            assert not rows or center_time_column in rows[0], f"Column '{center_time_column}' not found in metadata"
+            for row in rows:                                     # first row per id wins (ncwv:207 .iloc[0])
+                self._center_time.setdefault(row.get("id"), row.get(center_time_column))
+
+    def __len__(self):
+        return len(self.video_paths)
+
+    def _center(self, idx):
+        """ncwv:198-211: None when the id is unknown or the value is NaN / missing."""
+        v = self._center_time.get(self.video_ids[idx])
+        try:
+            return None if v is None or v != v else float(v)
+        except (TypeError, ValueError):
+            return None
+
+    def __getitem__(self, idx):
+        label, vid = self.labels[idx], self.video_ids[idx]
+        need = self.fps * self.duration
+        try:
+            reader = self.decoder(self.video_paths[idx])
+            n = len(reader)
+            ts, vfps = None, 0.0
+            if self.sample_strategy == "metadata_center":
+                ts = self._center(idx)
+                if self.video_fps_lookup:
+                    vfps = float(self.video_fps_lookup(self.video_paths[idx]))
+                else:                                            # ncwv:107-116: 30.0 when the container does not say
+                    get = getattr(reader, "get_avg_fps", None)
+                    vfps = float(get()) if get is not None else 30.0
+                    vfps = vfps if vfps > 0 else 30.0
+            start = select_start_frame(n, need, self.sample_strategy, random, ts, vfps)
+            indices = list(range(start, min(start + need, n)))
+            frames = _to_uint8_array(reader.get_batch(indices))
+            if len(frames) < need:                               # ncwv:213-227
+                if len(frames) > 0:
+                    frames = np.concatenate([frames, np.repeat(frames[-1][None], need - len(frames), axis=0)], axis=0)
+                else:
+                    frames = np.zeros((need, 720, 1280, 3), np.uint8)
+            frames = torch.from_numpy(np.ascontiguousarray(frames[:need]))
+            if self.defer:
+                t = self.transform
+                params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
+                return {"frames_u8": frames, "params": params, "target": label, "id": vid, "need": need}
+            video = frames.permute(3, 0, 1, 2)                  # ncwv:172
+            video = self.transform(video) if self.transform else video.float() / 255.0
+            frames = video.permute(1, 2, 3, 0)                  # ncwv:181
+        except Exception:
+            if self.defer:
+                return {"frames_u8": None, "params": None, "target": label, "id": vid, "need": need}
+            size = (224, 224) if self.transform else (720, 1280)   # ncwv:183-190
+            frames = torch.zeros(need, size[0], size[1], 3)
+        return {"frames": frames, "target": label, "id": vid}
+
+
 def deferred_collate(items: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
-    """collate_fn for ``defer=True`` datasets: stacks what stacks, keeps params / failures as lists."""
+    """collate_fn for ``defer=True`` datasets: stacks what stacks, keeps params / failures as lists.  'sensor' is
+    present for the NvidiaDashcamDataset protocol only."""
     ok = [it["frames_u8"] is not None for it in items]
     good = [it["frames_u8"] for it, k in zip(items, ok) if k]
-    return {
+    batch = {
         "frames_u8": torch.stack(good) if good else None,
         "valid": ok,
         "params": [it["params"] for it, k in zip(items, ok) if k],
-        "sensor": torch.stack([it["sensor"] for it in items]),
         "target": [it["target"] for it in items],
         "id": [it["id"] for it in items],
+        "need": items[0].get("need") if items else None,
     }
+    if items and all("sensor" in it for it in items):
+        batch["sensor"] = torch.stack([it["sensor"] for it in items])
+    return batch
 
 
 class GpuAugLoader:
@@ -245,10 +331,12 @@ class GpuAugLoader:
                     out = torch.zeros((n,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
                     out[torch.tensor(valid, device=self.device)] = res
             else:
-                t = batch["sensor"].shape[1]
+                t = batch["need"] if batch.get("need") else batch["sensor"].shape[1]
                 out = torch.zeros((n, 3, t, cs, cs), dtype=self.out_dtype or tf.out_dtype, device=self.device)
-            yield {"frames": out.permute(0, 2, 3, 4, 1), "sensor": batch["sensor"], "target": batch["target"],
-                   "id": batch["id"]}
+            res_batch = {"frames": out.permute(0, 2, 3, 4, 1), "target": batch["target"], "id": batch["id"]}
+            if "sensor" in batch:
+                res_batch["sensor"] = batch["sensor"]
+            yield res_batch
 
 
 def shard_clips(n_clips: int, rank: int, world: int) -> range:
