@@ -138,7 +138,9 @@ size_t nexar_workspace_bytes(const NexarPlan* plan, int32_t n_clips, int32_t fra
 /* Exact requirement for a batch whose NexarTransformArgs.any_flags is known (no augmentation: a few KB). */
 size_t nexar_workspace_bytes_for(const NexarPlan* plan, int32_t n_clips, int32_t frames_per_clip, uint32_t any_flags);
 
-/* The hot path.  Enqueues the kernels on args->stream and returns. */
+/* The hot path.  Enqueues the kernels on args->stream and returns.  Limits: n_clips * frames_per_clip <= 65535 per
+ * call (split larger batches), and, for augmented batches, one frame of the destination must span < 2^31 elements
+ * (2 * |dst_stride[1]| + (canvas - 1) * (|dst_stride[3]| + |dst_stride[4]|)); both return NEXAR_ERR_UNSUPPORTED. */
 int nexar_clip_transform(const NexarPlan* plan, const NexarTransformArgs* args);
 
 /* Number of kernel launches the last nexar_clip_transform call on this thread enqueued. */

@@ -1837,6 +1837,8 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   if (!p || !a) return fail(NEXAR_ERR_INVALID, "clip_transform: null argument");
   if (a->struct_size != sizeof(NexarTransformArgs)) return fail(NEXAR_ERR_INVALID, "clip_transform: NexarTransformArgs size mismatch (ABI)");
   if (a->n_clips <= 0 || a->frames_per_clip <= 0) return fail(NEXAR_ERR_INVALID, "clip_transform: empty batch");
+  if ((int64_t)a->n_clips * a->frames_per_clip > 65535)  // frames are a grid dimension (y / z): split larger batches
+    return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: more than 65535 frames in one call");
   if (!a->src || !a->frame_offsets || !a->params || !a->dst) return fail(NEXAR_ERR_INVALID, "clip_transform: null buffer");
   if (a->dst_dtype != NEXAR_DST_F32 && a->dst_dtype != NEXAR_DST_BF16) return fail(NEXAR_ERR_INVALID, "clip_transform: bad dst_dtype");
   const size_t need = nexar_workspace_bytes_for(p, a->n_clips, a->frames_per_clip, a->any_flags);
