@@ -223,7 +223,7 @@ def main():
     ap.add_argument("--mode", default="custom", choices=sorted(KW))
     ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step for --impl reference")
-    ap.add_argument("--cpu-clips", type=int, default=64, help="clips for the cpu_baseline leg (about 10-20 s of CPU work)")
+    ap.add_argument("--cpu-clips", type=int, default=128, help="clips for the cpu_baseline leg (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
