@@ -151,8 +151,12 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     sample = max(1, args.ref_clips)
     cps_runs = []
-    for _ in range(args.warmup):
-        cpu_port_clips_per_s(args.mode, t, h, w, cs, 1, cores)
+    per_clip = None
+    for _ in range(max(1, args.warmup)):
+        cps1, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, 1, cores)
+        per_clip = 1.0 / cps1
+    # bounded sample: the whole --steps run stays within about two minutes whatever K the driver passes
+    sample = max(1, min(sample, int(120.0 / (max(1, args.steps) * per_clip))))
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
         cps, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, sample, cores)
