@@ -761,19 +761,8 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-#ifndef NEXAR_L1PF
-#define NEXAR_L1PF 0  // row pairs ahead of the register loads that are pulled into L1 (0 = off; measured: no gain)
-#endif
-__device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) {
-#if NEXAR_L1PF > 0
-  return __ldg((const uint4*)(base + off));
-#else
-  return __ldcs((const uint4*)(base + off));
-#endif
-}
-__device__ __forceinline__ void l1_prefetch(const char* base, unsigned off) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(base + off));
-}
+// streaming 128-bit load of source bytes (evict-first: every byte is used once)
+__device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) { return __ldcs((const uint4*)(base + off)); }
 
 #ifndef NEXAR_MINB
 #define NEXAR_MINB 3
