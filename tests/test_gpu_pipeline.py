@@ -142,3 +142,31 @@ def test_host_pipeline_equals_device_path():
     r2 = pipe.wait(t2).clone()
     same = bool(torch.equal(r1, want)) and bool(torch.equal(r2, want2))
     assert same
+
+
+def test_integration_md_ctypes_example_runs():
+    """INTEGRATION.md section B is the binding a reference maintainer would write against the C ABI: execute it as
+    written (with a smaller batch) and compare with the Python host on the same frames."""
+    import os
+    import re
+    from vision_collision_detection_b200 import create_video_transforms
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    section = text[text.index("## B."):]
+    code = re.search(r"```python\n(.*?)```", section, re.S).group(1)
+    code = code.replace("B, T = 32, 16", "B, T = 2, 3")
+    code = code.replace('C.CDLL("vision_collision_detection_b200/libnexar_clip_b200.so")',
+                        'C.CDLL(%r)' % os.path.join(root, "vision_collision_detection_b200", "libnexar_clip_b200.so"))
+    code = code.replace('frames = torch.empty((B, T, 720, 1280, 3), dtype=torch.uint8, device="cuda")',
+                        'frames = FRAMES')
+    from vision_collision_detection_b200.synth import make_clip_torch
+    frames = torch.stack([make_clip_torch(3, 720, 1280, seed=s, kind="dashcam", device="cuda") for s in (1, 2)])
+    ns = {"FRAMES": frames}
+    exec(compile(code, "INTEGRATION.md#B", "exec"), ns)
+    torch.cuda.synchronize()
+    got = ns["out"]
+    tf = create_video_transforms(mode="val", out_dtype=torch.bfloat16)
+    want = tf.forward_batch(frames)
+    assert tuple(got.shape) == (2, 3, 3, 224, 224) and got.dtype == torch.bfloat16
+    same = bool(torch.equal(got, want))
+    assert same
