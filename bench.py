@@ -28,7 +28,7 @@ import torch  # noqa: E402
 WORKLOADS = {
     # name: (clips per GPU, T, H, W, crop_size)
     "cfg2": (32, 16, 720, 1280, 224),
-    "cfg3": (32, 32, 720, 1280, 320),
+    "cfg3": (256, 32, 720, 1280, 320),  # BASELINE configs[2]: ONE 256-clip batch, sharded over the GPUs (strong scaling)
     "tiny": (4, 4, 180, 320, 112),
     "cfg2s": (8, 16, 720, 1280, 224),   # a trainer-sized batch (cfg5 uses 8 clips per GPU): band-count tuning
     # BASELINE configs[3]: one 40 s x 30 fps 720p video, val chain, every frame transformed once,
@@ -50,12 +50,12 @@ def algorithmic_bytes_per_clip(t, h, w, cs, out_bytes):
     return t * h * w * 3 + 3 * t * cs * cs * out_bytes
 
 
-def ncu_traffic(mode):
-    """dram bytes per launch of the resize kernel from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+def ncu_traffic(workload, mode, out_dtype):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(mode)
+            return json.load(f).get(f"{workload}:{mode}:{out_dtype}")
     except Exception:
         return None
 
@@ -128,7 +128,7 @@ def oracle_setup(mode, cs):
 
 
 def cpu_port_clips_per_s(mode, t, h, w, cs, n_clips, threads):
-    """Time the CPU port of the reference transform (oracle/torch_port.py) on ``n_clips`` clips."""
+    """Time the CPU port of the reference transform (oracle/torch_port.py) on ``n_clips`` clips, one process."""
     from oracle import torch_port as P
     from vision_collision_detection_b200.synth import make_clip_np
     torch.set_num_threads(threads)
@@ -143,33 +143,148 @@ def cpu_port_clips_per_s(mode, t, h, w, cs, n_clips, threads):
     return n_clips / dt, dt
 
 
+_WORKER_SRC = r"""
+import os, sys, time, random
+sys.path.insert(0, {root!r})
+import torch
+torch.set_num_threads({threads})
+from oracle import torch_port as P, np_oracle as O
+from vision_collision_detection_b200.synth import make_clip_np
+mode, t, h, w, cs = {mode!r}, {t}, {h}, {w}, {cs}
+aug = O.AugConfig(rotation_range=(-5, 5)) if mode == "custom" else O.AugConfig()
+cfg = O.TransformConfig(mode="val" if mode == "val" else "train", crop_size=cs,
+                        enable_custom_augmentation=(mode == "custom"), aug=aug)
+clip = torch.from_numpy(make_clip_np(t, h, w, 0, "dashcam")).permute(3, 0, 1, 2)
+random.seed(1234 + {wid})
+P.clip_transform(clip[:, :2], cfg, random)
+print("ready", flush=True)
+for line in sys.stdin:                  # "go N": the start gun, every worker begins its N timed clips together
+    parts = line.split()
+    if not parts or parts[0] != "go":
+        break
+    t0 = time.time()
+    for _ in range(int(parts[1])):
+        P.clip_transform(clip, cfg, random)
+    print("done %.6f %.6f" % (t0, time.time()), flush=True)
+"""
+
+
+class CpuWorkerPool:
+    """The reference's deployment shape (nexar_complete_with_validation.py:49-51, nexar_train_distributed.py:97):
+    ``n_workers`` DataLoader-style processes with OMP_NUM_THREADS=``threads`` each, every worker transforming its own clips."""
+
+    def __init__(self, mode, t, h, w, cs, n_workers, threads):
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+        self.procs = []
+        for wid in range(n_workers):
+            src = _WORKER_SRC.format(root=ROOT, threads=threads, mode=mode, t=t, h=h, w=w, cs=cs, wid=wid)
+            self.procs.append(subprocess.Popen([sys.executable, "-c", src], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                               stderr=subprocess.DEVNULL, text=True, env=env))
+        for p in self.procs:
+            if not p.stdout.readline().startswith("ready"):
+                self.close()
+                raise RuntimeError("cpu worker failed to start")
+
+    def run(self, clips_per_worker):
+        """-> (aggregate clips/s, seconds) over the span from the common start to the last worker's finish."""
+        for p in self.procs:
+            p.stdin.write(f"go {clips_per_worker}\n")
+            p.stdin.flush()
+        t0s, t1s = [], []
+        for p in self.procs:
+            parts = p.stdout.readline().split()
+            t0s.append(float(parts[1]))
+            t1s.append(float(parts[2]))
+        dt = max(t1s) - min(t0s)
+        return len(self.procs) * clips_per_worker / dt, dt
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close()
+                p.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                p.kill()
+        self.procs = []
+
+
+def cpu_legs(mode, t, h, w, cs, budget_s=24.0):
+    """BASELINE.md section 4's three CPU settings on this box, bounded to about ``budget_s`` seconds of wall time:
+    (i) one process with every core as torch threads, (ii) P = cores/4 worker processes x 4 threads (the reference's
+    real DataLoader deployment), (iii) one thread.  Returns (best value, legs dict)."""
+    cores = os.cpu_count() or 1
+    probe, dtp = cpu_port_clips_per_s(mode, t, h, w, cs, 1, cores)
+    n_all = max(2, min(256, int(budget_s * 0.4 * probe)))
+    all_cps, all_dt = cpu_port_clips_per_s(mode, t, h, w, cs, n_all, cores)
+    legs = {"all_threads": {"value": all_cps, "procs": 1, "threads": cores, "clips": n_all, "seconds": round(all_dt, 2)}}
+    nw = max(1, cores // 4)
+    try:
+        # a worker with 4 threads is roughly (4 / cores) of the all-thread rate or better; size for ~0.4 of the budget
+        per_worker = max(1, int(budget_s * 0.4 * all_cps / nw * 1.5))
+        pool = CpuWorkerPool(mode, t, h, w, cs, nw, 4)
+        try:
+            w_cps, w_dt = pool.run(per_worker)
+        finally:
+            pool.close()
+        legs["workers"] = {"value": w_cps, "procs": nw, "threads": 4, "clips": nw * per_worker, "seconds": round(w_dt, 2),
+                           "as": "nexar_complete_with_validation.py:49-51 (OMP_NUM_THREADS=4 per DataLoader worker)"}
+    except Exception as e:  # noqa: BLE001
+        legs["workers"] = {"value": None, "error": str(e)[:100]}
+    n_one = max(1, min(16, int(budget_s * 0.15 * all_cps / max(1.0, cores / 3.0))))
+    one_cps, one_dt = cpu_port_clips_per_s(mode, t, h, w, cs, n_one, 1)
+    torch.set_num_threads(cores)
+    legs["single_thread"] = {"value": one_cps, "procs": 1, "threads": 1, "clips": n_one, "seconds": round(one_dt, 2)}
+    best = max((v for v in (legs["all_threads"]["value"], legs["workers"].get("value")) if v), default=all_cps)
+    return best, legs
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (the oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU path (the oracle port) on the host cores, rank 0 only.  Each step is a
+    bounded sample of the workload; the faster of the two multi-core settings (all-thread process / cores/4 workers x 4
+    threads, the reference's DataLoader shape) is the step's configuration, chosen in the warm-up."""
     if rank != 0:
         return
     b, t, h, w, cs = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample = max(1, args.ref_clips)
-    cps_runs = []
-    per_clip = None
-    for _ in range(max(1, args.warmup)):
-        cps1, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, 1, cores)
-        per_clip = 1.0 / cps1
+    nw = max(1, cores // 4)
+    probe, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, 1, cores)
+    for _ in range(max(0, args.warmup - 1)):
+        probe, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, 1, cores)
+    pool = None
+    try:
+        pool = CpuWorkerPool(args.mode, t, h, w, cs, nw, 4)
+        wprobe, _ = pool.run(1)
+    except Exception:  # noqa: BLE001
+        wprobe = 0.0
+    use_workers = wprobe > probe
+    rate = max(wprobe, probe)
     # bounded sample: the whole --steps run stays within about two minutes whatever K the driver passes
-    sample = max(1, min(sample, int(120.0 / (max(1, args.steps) * per_clip))))
+    per_step_s = min(20.0, 120.0 / max(1, args.steps))
+    if use_workers:
+        per_worker = max(1, int(per_step_s * rate / nw))
+        sample_desc = f"{nw} worker processes x 4 threads, {per_worker} clip(s) of {t}x{h}x{w} each per step"
+    else:
+        sample = max(1, min(max(1, args.ref_clips), int(per_step_s * rate)))
+        sample_desc = f"{sample} clip(s) of {t}x{h}x{w} per step, one process, torch threads={cores}"
+    cps_runs = []
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        cps, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, sample, cores)
+        if use_workers:
+            cps, _ = pool.run(per_worker)
+        else:
+            cps, _ = cpu_port_clips_per_s(args.mode, t, h, w, cs, sample, cores)
         cps_runs.append(cps)
     wall = time.perf_counter() - t_all0
+    if pool is not None:
+        pool.close()
     value = float(np.mean(cps_runs))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}:{args.mode} {t}x{h}x{w} u8 -> {cs}x{cs} f32 on host CPU"},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} clip(s) of {t}x{h}x{w} per step, torch threads={cores}"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample_desc,
+                         "probe_all_threads": probe, "probe_workers": wprobe},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,12 +341,12 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="custom", choices=sorted(KW))
     ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step for --impl reference")
-    ap.add_argument("--cpu-clips", type=int, default=128, help="clips for the cpu_baseline leg (about 10-20 s of CPU work)")
+    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step for --impl reference (one-process setting)")
+    ap.add_argument("--cpu-seconds", type=float, default=24.0, help="wall-time budget of the cpu_baseline legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup   # timing rules: W >= 3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,6 +369,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     b, t, h, w, cs = WORKLOADS[args.workload]
+    scaling = "weak"
+    if args.workload == "cfg3":
+        # BASELINE configs[2] as written: ONE batch of 256 clips sharded over the GPUs (256 / 128 / 64 / 32 per GPU)
+        if b % world:
+            raise SystemExit(f"cfg3 shards {b} clips evenly: --gpus must divide {b}")
+        b //= world
+        scaling = "strong"
     out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
     if args.workload == "cfg4":
         return run_cfg4(args, rank, world, dev, out_dtype)
@@ -262,9 +384,18 @@ def main():
     if os.environ.get("NEXAR_FAST_BANDS"):
         from vision_collision_detection_b200 import _lib as _l
         _l.lib().nexar_set_fast_bands(int(os.environ["NEXAR_FAST_BANDS"]))
+    if os.environ.get("NEXAR_RESIZE_VARIANT"):      # experiments: 2 = the unfused K1 + K1.5 + K2 + K3 path
+        from vision_collision_detection_b200 import _lib as _l
+        _l.lib().nexar_set_resize_kernel(int(os.environ["NEXAR_RESIZE_VARIANT"]))
 
-    # synthetic device-resident shard (1.4 GB for cfg2: larger than the 126 MB L2, so every step streams from HBM)
-    clips = torch.stack([make_clip_torch(t, h, w, seed=rank * 1000 + i, kind="dashcam", device=dev) for i in range(b)])
+    # synthetic device-resident shard (1.4 GB for cfg2: larger than the 126 MB L2, so every step streams from HBM);
+    # at most 32 distinct clips are synthesised, larger shards repeat them
+    n_distinct = min(b, 32)
+    clips = torch.empty((b, t, h, w, 3), dtype=torch.uint8, device=dev)
+    for i in range(n_distinct):
+        clips[i] = make_clip_torch(t, h, w, seed=rank * 1000 + i, kind="dashcam", device=dev)
+    for i in range(n_distinct, b):
+        clips[i] = clips[i % n_distinct]
     out = torch.empty((b, 3, t, cs, cs), dtype=out_dtype, device=dev)
     random.seed(1234 + rank)
     param_sets = [tf.sample_params(b, h, w) for _ in range(4)]
@@ -278,17 +409,18 @@ def main():
         tf.forward_batch(clips, params=param_sets[i % len(param_sets)], out=out)
 
     # ---- device-resident timing ("value") ------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.2 s to stream
-    # warm-up: the W steps asked for, and at least 10 steps / 50 ms so that the clocks have ramped and the one-time
-    # costs (plan tables, workspace, pinned parameter ring) are behind us even when W is tiny; "warmup" reports the count
+    sampler = ClockSampler(local) if rank == 0 else None   # started early: nvidia-smi needs ~0.2 s to stream
+    # Pre-heat (NOT steps of the transform): ~60 ms of plain torch copies so the SM clock has ramped before the W
+    # warm-up steps the driver asked for; the warm-up itself is exactly --warmup steps (plan tables, workspace and the
+    # pinned parameter ring are created in its first step).
+    scratch = torch.empty_like(clips[: max(1, min(b, 8))])
     t_w = time.time()
-    n_warm = 0
-    while n_warm < max(args.warmup, 10) or (time.time() - t_w < 0.05 and n_warm < 1000):
-        step(n_warm)
-        n_warm += 1
-        if n_warm % 8 == 0:
-            torch.cuda.synchronize()
-    args.warmup = n_warm
+    while time.time() - t_w < 0.06:
+        scratch.copy_(clips[: scratch.shape[0]])
+        torch.cuda.synchronize()
+    del scratch
+    for i in range(args.warmup):
+        step(i)
     barrier()
     from vision_collision_detection_b200 import _lib
     _lib.lib().nexar_profile_begin(args.steps + 8)
@@ -326,64 +458,84 @@ def main():
     # ---- end to end: pinned host clips -> H2D -> transform -> D2H (through the public host API) ----
     e2e = None
     if not args.no_e2e:
-        pipe = HostClipPipeline(tf, n_clips=b, frames=t, height=h, width=w, device=dev)
+        eb = min(b, 32)                            # host batch of the e2e leg (pinned memory: 44-88 MB per clip)
+        pipe = HostClipPipeline(tf, n_clips=eb, frames=t, height=h, width=w, device=dev)
         host_in = pipe.pinned_input()
-        host_in.copy_(clips.cpu())
+        host_in.copy_(clips[:eb].cpu())
         e2e_steps = max(3, min(args.steps, 8))
         host_in2 = pipe.pinned_input()          # two input batches alternate: one is being copied while the next is "decoded"
         host_in2.copy_(host_in)
         ins = [host_in, host_in2]
         for i in range(2):
-            pipe.run(ins[i & 1], params=param_sets[i % len(param_sets)])
+            pipe.run(ins[i & 1], params=param_sets[i % len(param_sets)][:eb])
         barrier()
         ts0 = time.perf_counter()
         e0.record()
         prev = None
         for i in range(e2e_steps):                # steady state: batch i+1 is submitted before batch i is collected
-            ticket = pipe.submit(ins[i & 1], params=param_sets[i % len(param_sets)])
+            ticket = pipe.submit(ins[i & 1], params=param_sets[i % len(param_sets)][:eb])
             if prev is not None:
                 host_out = pipe.wait(prev)
             prev = ticket
         host_out = pipe.wait(prev)
         e1.record()
-        barrier()
+        torch.cuda.synchronize()
         wall = time.perf_counter() - ts0
-        ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+        own_ms = max(e0.elapsed_time(e1), wall * 1e3) / e2e_steps
+        barrier()
+        ems = torch.tensor([own_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * b / (float(ems.item()) / e2e_steps * 1e-3), "unit": "clips/s",
+        h2d_rank = torch.tensor([host_in.numel() / (own_ms * 1e-3) / 1e9], device=dev, dtype=torch.float64)
+        h2d_all = [torch.zeros_like(h2d_rank) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(h2d_all, h2d_rank)
+        else:
+            h2d_all = [h2d_rank]
+        e2e = {"value": world * eb / (float(ems.item()) * 1e-3), "unit": "clips/s",
                "h2d_bytes_per_step": int(host_in.numel()), "d2h_bytes_per_step": int(host_out.numel() * host_out.element_size()),
-               "steps": e2e_steps}
+               "steps": e2e_steps, "clips_per_gpu_per_step": eb,
+               "h2d_GBs_per_gpu": [round(float(x.item()), 2) for x in h2d_all],
+               "h2d_GBs_aggregate": round(sum(float(x.item()) for x in h2d_all), 2),
+               "note": "uint8 source over PCIe (44 MB per cfg2 clip) bounds this leg; see DESIGN.md (F1: NV12 source halves it)"}
         del pipe, host_in, host_in2, ins
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         per_clip = algorithmic_bytes_per_clip(t, h, w, cs, out.element_size())
-        # dominant kernel: the resize pass (K1).  Its algorithmic bytes: source read once + what it writes
-        # (final output when no clip is augmented, else the fp32 RGBX intermediate of the content box).
-        k1_ms_avg = (sum(k1_ms) / len(k1_ms)) if k1_ms else None
-        k1_bytes = b * per_clip
-        roof = None
-        if k1_ms_avg:
-            ach = k1_bytes / (k1_ms_avg * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "resize (K1)", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "frac_of_8TBs_nominal": ach / 8000.0, "peak_kind": peak_kind,
-                    "kernel_ms": k1_ms_avg, "kernel_share_of_step": k1_ms_avg / ms_step,
-                    "algorithmic_bytes_per_launch": k1_bytes, "traffic": ncu_traffic(args.mode) if (args.workload == "cfg2" and args.out_dtype == "bf16") else None,
-                    "step_achieved_GBs": b * per_clip / (ms_step * 1e-3) / 1e9}
+        step_bytes = b * per_clip
+        step_ach = step_bytes / (ms_step * 1e-3) / 1e9
+        # dominant kernel: resize_fast_kernel.  With augmentation it is the fused cluster kernel (resize + colour + affine +
+        # normalise + store = the whole transform of the batch); without, the resize + normalise + store kernel.  Either way
+        # its algorithmic bytes are the step's: source read once + output written once.
+        k_ms = (sum(k1_ms) / len(k1_ms)) if k1_ms else None
+        kern = None
+        if k_ms:
+            k_ach = step_bytes / (k_ms * 1e-3) / 1e9
+            kern = {"name": "resize_fast_kernel" + (" (fused: resize+colour+affine+normalise)" if args.mode == "custom" else ""),
+                    "ms": k_ms, "achieved": k_ach, "frac": k_ach / peaks["hbm_gbs"], "share_of_step": k_ms / ms_step,
+                    "timed": "CUDA event pair around the launch on its stream, every timed step (nexar_profile_begin/end)"}
+        # roofline.frac is STEP level (all launches of the step, device events): it is never better than the kernel's own
+        roof = {"bound": "hbm", "achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_ach / peaks["hbm_gbs"],
+                "frac_of_8TBs_nominal": step_ach / 8000.0, "peak_kind": peak_kind, "level": "step (every launch of the step)",
+                "algorithmic_bytes_per_step": step_bytes, "kernel": kern,
+                "traffic": ncu_traffic(args.workload, args.mode, args.out_dtype)}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cps, dt = cpu_port_clips_per_s(args.mode, t, h, w, cs, args.cpu_clips, cores)
-            cpu = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_clips} clips of {t}x{h}x{w} ({dt:.1f} s), oracle/torch_port.py, torch threads={cores}"}
+            best, legs = cpu_legs(args.mode, t, h, w, cs, args.cpu_seconds)
+            cpu = {"value": best, "unit": "clips/s", "cores": cores, "kind": "port",
+                   "sample": f"oracle/torch_port.py on {t}x{h}x{w} clips; value = the faster multi-core setting; legs list clips and seconds",
+                   "legs": legs}
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": f"u8 -> i32 fixed-point (15-bit taps) / f32 -> {args.out_dtype}", "data": "synthetic",
             "config": {"workload": f"{args.workload}:{args.mode} {b} clips/GPU x {t}x{h}x{w} u8 -> {cs}x{cs} {args.out_dtype}",
                        "kwargs": "nexar_videos.py:2003-2010" if args.mode == "custom" else args.mode,
-                       "l2": "input 1.4 GB/step > 126 MB L2 (no flush needed)", "sharding": f"{b} clips per GPU, no collective"},
+                       "l2": f"input {b * t * h * w * 3 / 1e9:.1f} GB/step > 126 MB L2 (no flush needed)",
+                       "sharding": f"{b} clips per GPU, no collective" + (" (one 256-clip batch split over the GPUs)" if scaling == "strong" else ""),
+                       "preheat": "60 ms of torch copies before the warm-up (clock ramp; not transform steps)"},
             "output_GBs": world * b * 3 * t * cs * cs * out.element_size() / (ms_step * 1e-3) / 1e9,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

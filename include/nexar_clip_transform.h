@@ -152,9 +152,11 @@ int nexar_last_launch_count(void);
 int nexar_profile_begin(int32_t max_calls);
 int nexar_profile_end(float* ms_out, int32_t cap);
 
-/* Tuning knobs for experiments: resize kernel (0 = auto, 1 = force the general fp32 kernel, 2 = the
- * register-prefetch variant of the fast kernel instead of the TMA-ring one) and the
- * number of row bands each frame is split into by the fast kernel (0 = auto). */
+/* Tuning knobs for experiments, per calling thread (the library keeps no process-global mutable state; the profile
+ * events above are per thread too).  Resize kernel: 0 = auto (the fixed-point fast kernel when the geometry allows it,
+ * followed by the colour and geometry kernels for augmented clips), 1 = force the general fp32 kernels, 4 = augmented
+ * batches take the fused thread-block-cluster kernel (resize + colour + geometry in one launch).  Bands: the number of
+ * row bands each frame is split into by the fast kernel (0 = auto). */
 int nexar_set_resize_kernel(int32_t variant);
 int nexar_set_fast_bands(int32_t bands);
 

@@ -3,13 +3,13 @@
 // Path (reference file:line in include/nexar_clip_transform.h):
 //   K1 resize   : uint8 THWC frames -> antialiased separable resample -> either the
 //                 final normalised tensor (no augmentation) or a brightness-adjusted
-//                 fp32 RGBX intermediate + per-band gray sums (augmentation).
+//                 8-byte intermediate pixel + per-band gray sums (augmentation).
 //   K2 colour   : contrast (needs the frame's gray mean) -> saturation -> hue, in place.
 //   K3 geometry : affine gather with the fill=0 mask quirk, effects, normalise, store.
 //   K4 blur     : only when blur_sigma > 0 (reflect-padded gaussian, then the rest of the chain).
 // The /255 decision of VideoTransform.forward is clip-global and data dependent
 // (nexar_video_aug.py:814): K1 runs assuming "max > 1", records the clip maximum, and
-// a second, normally empty, launch redoes the clips whose maximum was <= 1.
+// a second, normally empty, launch (fixup_frame_kernel) redoes the clips whose maximum was <= 1.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 
@@ -27,11 +27,12 @@
 // ---------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-static int g_resize_variant = 0;  // 0 auto (register-prefetch fast kernel), 1 force the general kernel, 3 TMA-ring fast kernel
-static int g_fast_bands = 0;      // 0 auto
+// experiment knobs and the optional kernel timing are per calling thread (the library keeps no process-global mutable state)
+static thread_local int g_resize_variant = 0;  // 0 auto, 1 force the general fp32 kernels, 4 fused cluster kernel for augmented batches
+static thread_local int g_fast_bands = 0;      // 0 auto
 
-static std::vector<cudaEvent_t> g_prof_ev;
-static int g_prof_n = 0;
+static thread_local std::vector<cudaEvent_t> g_prof_ev;
+static thread_local int g_prof_n = 0;
 
 static inline int imin_host(int a, int b) { return a < b ? a : b; }
 
@@ -422,7 +423,7 @@ struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
   unsigned long long* gray_partial;  // [2][n_frames][kMaxBands] fixed-point (2^-22) gray sums: exact, order-independent
   FrameInfo* finfo;     // [n_frames] per-frame constants for K2/K3, written by K1.5
-  float4* inter;        // [n_frames][bh][bw]   RGBX, brightness-adjusted then colour-adjusted in place
+  uint2* inter;         // [n_frames][bh][bw]   q15 RGBX pixels (8 bytes), brightness-adjusted, then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
   size_t total;
 };
@@ -439,8 +440,8 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base, unsig
   off = align_up(off + 2 * nf * kMaxBands * sizeof(unsigned long long), 256);
   w.finfo = (FrameInfo*)(b + off);
   off = align_up(off + nf * sizeof(FrameInfo), 256);
-  w.inter = (float4*)(b + off);  // only augmented clips use it
-  if (any_flags & NEXAR_AUG) off = align_up(off + nf * bh * bw * sizeof(float4), 256);
+  w.inter = (uint2*)(b + off);  // only augmented clips use it
+  if (any_flags & NEXAR_AUG) off = align_up(off + nf * bh * bw * sizeof(uint2), 256);
   w.canvas = (float*)(b + off);  // only the blur path uses it
   if (any_flags & NEXAR_BLUR) off = align_up(off + nf * 3 * (size_t)p->g.canvas * p->g.canvas * sizeof(float), 256);
   w.total = off;
@@ -472,7 +473,7 @@ struct KArgs {
   unsigned* clip_max;
   unsigned long long* gray_partial;
   FrameInfo* finfo;
-  float4* inter;
+  uint2* inter;
   float* canvas;
   int n_frames;
   int bh, bw;  // allocation dims of one intermediate frame
@@ -630,11 +631,11 @@ __global__ void clip_max_kernel(DevPlan P, KArgs A) {
 // K1 (general variant): output-stationary separable resample.  Any geometry
 // (down- or up-scale, any width), uint8 or float32 source.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 pack_q21(float r, float g, float b);
+
 template <typename SrcT, typename DstT>
-__global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A) {
-  extern __shared__ float vbuf[];  // [src_w*3] vertical-pass result of the current resized row
-  __shared__ unsigned long long red[32];
-  const int frame = blockIdx.y;
+__device__ __forceinline__ void resize_general_body(const DevPlan& P, const KArgs& A, int frame, int band, int nb, float* vbuf,
+                                                    unsigned long long* red) {
   const int clip = frame / A.T;
   const int t = frame - clip * A.T;
   const NexarClipParams* cp = A.params + clip;
@@ -649,7 +650,6 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
   }
   const bool flip = flags & NEXAR_FLIP, aug = flags & NEXAR_AUG;
   const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flip);
-  const int nb = gridDim.x, band = blockIdx.x;
   const int per = (B.i_hi - B.i_lo + nb - 1) / nb;
   const int i0 = min(B.i_hi, B.i_lo + band * per), i1 = min(B.i_hi, i0 + per);
   const char* fbase = (const char*)A.src + A.frame_offsets[frame];
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
         g = clamp01(__fmul_rn(bright, g));
         b = clamp01(__fmul_rn(bright, b));
         gsum += gray_fix(r, g, b);
-        A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (x - B.bx0)] = make_float4(r, g, b, 0.0f);
+        A.inter[((size_t)frame * A.bh + (y - B.by0)) * A.bw + (x - B.bx0)] = pack_q21(r, g, b);
       } else {
         const int64_t o = dbase + (int64_t)y * A.sy + (int64_t)x * A.sx;
         store_out<DstT>(A.dst, o, fmaf(r, nsc[0], nbi[0]));
@@ -737,6 +737,13 @@ __global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A)
   }
 }
 
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256) resize_general_kernel(DevPlan P, KArgs A) {
+  extern __shared__ float vbuf[];  // [src_w*3] vertical-pass result of the current resized row
+  __shared__ unsigned long long red[32];
+  resize_general_body<SrcT, DstT>(P, A, blockIdx.y, blockIdx.x, gridDim.x, vbuf, red);
+}
+
 
 // ---------------------------------------------------------------------------------
 // K1 (fast variant): input-stationary fixed-point vertical pass + fixed-point horizontal pass, both on dp2a.
@@ -767,9 +774,6 @@ __device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) { ret
 #ifndef NEXAR_MINB
 #define NEXAR_MINB 3
 #endif
-#ifndef NEXAR_STAGES
-#define NEXAR_STAGES 6  // row pairs in flight per CTA in the TMA ring
-#endif
 #ifndef NEXAR_LOOKAHEAD
 #define NEXAR_LOOKAHEAD 4
 #endif
@@ -781,34 +785,71 @@ __device__ __forceinline__ uint4 ld_stream(const char* base, unsigned off) { ret
 #define NEXAR_E_BEGIN1 8u
 #define NEXAR_E_ROWSHIFT 4
 
-// ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------------
+// ---- mbarrier primitives ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0u;
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
                :: "r"(bar), "r"(parity) : "memory");
 }
-// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS UBLKCP)
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+
+// ---- the 8-byte intermediate pixel of augmented clips -----------------------------------------------------------
+// Stage 1 (K1 -> K2, brightness-adjusted): three 21-bit fixed-point channels packed into 64 bits (step 4.8e-7).
+// Stage 2 (K2 -> K3, colour-adjusted, "q15"): four uint16 (R, G, B, spare), each 0x8000 | round(v * 32767): with that
+// top bit set, ONE byte permute turns a stored value into the float 1 + q / 32768 (bits 0x3F800000 | q << 8), so the
+// affine gather pays one PRMT per sample instead of an integer-to-float conversion, and the constant 1 is taken out
+// once per pixel (see geometry_kernel).  Quantisation step 3.05e-5 of full scale (gate: 2.25e-4 after the division by std).
+constexpr float kQ21 = 2097151.0f;                  // 2^21 - 1
+constexpr float kQ21Inv = 1.0f / 2097151.0f;
+__device__ __forceinline__ uint2 pack_q21(float r, float g, float b) {
+  // float_bits(v * (2^21 - 1) + 2^23) = 0x4B000000 + round(v * (2^21 - 1))
+  const unsigned qr = __float_as_uint(fmaf(r, kQ21, 8388608.0f)) & 0x1FFFFFu;
+  const unsigned qg = __float_as_uint(fmaf(g, kQ21, 8388608.0f)) & 0x1FFFFFu;
+  const unsigned qb = __float_as_uint(fmaf(b, kQ21, 8388608.0f)) & 0x1FFFFFu;
+  return make_uint2(qr | (qg << 21), (qg >> 11) | (qb << 10));
+}
+__device__ __forceinline__ void unpack_q21(uint2 v, float& r, float& g, float& b) {
+  r = (float)(v.x & 0x1FFFFFu) * kQ21Inv;
+  g = (float)(__funnelshift_r(v.x, v.y, 21) & 0x1FFFFFu) * kQ21Inv;
+  b = (float)((v.y >> 10) & 0x1FFFFFu) * kQ21Inv;
+}
+constexpr float kQ15 = 32767.0f;
+constexpr float kQ15Magic = 8388608.0f + 32768.0f;  // low 16 bits of float_bits(v * 32767 + magic) = 0x8000 | round(v * 32767)
+constexpr float kQ15Inv = 32768.0f / 32767.0f;      // v = (F - 1) * kQ15Inv
+__device__ __forceinline__ uint2 pack_q15(float r, float g, float b) {
+  const unsigned qr = __float_as_uint(fmaf(r, kQ15, kQ15Magic));
+  const unsigned qg = __float_as_uint(fmaf(g, kQ15, kQ15Magic));
+  const unsigned qb = __float_as_uint(fmaf(b, kQ15, kQ15Magic));
+  return make_uint2(__byte_perm(qr, qg, 0x5410), qb & 0xFFFFu);
+}
+__device__ __forceinline__ float q15_r(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7104)); }
+__device__ __forceinline__ float q15_g(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7324)); }
+__device__ __forceinline__ float q15_b(uint2 v) { return __uint_as_float(__byte_perm(v.y, 0x3F000000u, 0x7104)); }
+
+// thread-block cluster barrier (all threads of all CTAs of the cluster); release/acquire at cluster scope orders the
+// global-memory writes before the arrive with the reads after the wait
+#ifndef NEXAR_EXP
+#define NEXAR_EXP 0   // timing experiments only: 1 skip phase B, 2 skip phase C, 4 CTA barriers instead of cluster barriers
+#endif
+__device__ __forceinline__ void cluster_sync_all() {
+  if (NEXAR_EXP & 4) { __syncthreads(); return; }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int KX, int NT, int MINB, int RS, typename DstT>
+template <typename DstT, int NT, bool CLUSTER>
+__device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KArgs& A, const NexarClipParams* cp,
+                                                      unsigned flags, int frame, int clip, int t, int band, int nb,
+                                                      const Box& B, int i0, int i1, int slot);
+
+// FUSED: the nb bands of a frame form one thread-block cluster; after the resize the cluster goes on, in the same
+// launch, with the colour chain (in place on the band's own rows) and the affine gather + store (see
+// fused_colour_geometry), so the augmented path is ONE kernel and the intermediate is consumed while it is L2-hot.
+template <int KX, int NT, int MINB, int RS, typename DstT, bool FUSED>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -865,14 +906,14 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     if (flip) xo = P.cs - 1 - xo;
     const float post = scale * (1.0f / (128.0f * 32768.0f));
     // where this frame's pixels go (uniform base; the per-thread column and the row are added per output row)
-    float4* const ibase = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;
+    uint2* const ibase = A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw - B.bx0;  // 8-byte q15 pixels
     DstT* const obase = (DstT*)A.dst + dbase;
 
     // ---- vertical pass state ----
     const unsigned rnd = 1u << 7;  // P.shift == 15: staging value = (acc + 128) >> 8
     unsigned acc0[16], acc1[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = 0u;
+    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = rnd;
     const int p0 = P.ystart[i0] >> 1;
     const int plast = (P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1;  // inclusive
     const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
@@ -972,7 +1013,7 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         g = clamp01(__fmul_rn(bright, g));                                                             \
         bl = clamp01(__fmul_rn(bright, bl));                                                           \
         gsum += gray_fix(r, g, bl);                                                                     \
-        ibase[y * A.bw + xo] = make_float4(r, g, bl, 0.0f);                                            \
+        ibase[y * A.bw + xo] = pack_q21(r, g, bl);                                                      \
       } else {                                                                                         \
         DstT* const o = obase + ((int64_t)y * A.sy + (int64_t)xo * A.sx);                              \
         if (A.normalize) {                                                                             \
@@ -1004,17 +1045,10 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       CA = ld_stream(ptr, (unsigned)(ROFF) * rs);                                                          \
       CB = ld_stream(ptr, (unsigned)(ROFF + 1) * rs);                                                      \
     }                                                                                                      \
-    if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
-      if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
-      if (ey) NEXAR_ACCUM(acc1, ey)                                                                      \
-    } else {                                                                                               \
-      if (ex) {                                                                                           \
-        if (ez & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, ex) else NEXAR_ACCUM(acc0, ex)                 \
-      }                                                                                                    \
-      if (ey) {                                                                                           \
-        if (ez & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, ey) else NEXAR_ACCUM(acc1, ey)                 \
-      }                                                                                                    \
-    }                                                                                                      \
+    /* both slots accumulate unconditionally (both are live in > 99 % of the pairs; an idle slot has zero taps): a   */ \
+    /* slot restarts from the rounding constant when its row is flushed below, so no begin / idle tests are needed    */ \
+    NEXAR_ACCUM(acc0, ex)                                                                                  \
+    NEXAR_ACCUM(acc1, ey)                                                                                  \
     if (pend >= 0) { /* the row staged by an earlier pair: by now every warp has arrived, the wait is free */ \
       mbar_wait(bar, phase);                                                                               \
       phase ^= 1u;                                                                                         \
@@ -1039,10 +1073,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
         pbuf = bufoff;                                                                                     \
         bufoff = vbytes - bufoff; /* other staging buffer */                                               \
       }                                                                                                    \
+      /* the flushed slot restarts: rounding constant + the first tap of its next row when that shares this pair */ \
       const unsigned wpost = ez & 0xFFFF0000u;                                                             \
-      if (wpost) { /* first tap of the slot's next row shares this pair */                                 \
-        if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                         \
-      }                                                                                                    \
+      if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                           \
     }                                                                                                      \
   }
 
@@ -1072,288 +1105,46 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
     const unsigned long long s = block_sum((unsigned long long)gsum, red);
     if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
   }
-}
-
-// K1 (TMA variant): same arithmetic as resize_fast_kernel, but the source rows arrive through an
-// NS-stage shared-memory ring filled by 1-D bulk copies (one row pair = one contiguous copy) that thread 0
-// issues and mbarriers track; every warp releases a stage as soon as its bytes are in registers.  No
-// per-thread global address arithmetic, no register prefetch, no L2 prefetch.
-template <int KX, int NT, int MINB, int NS, typename DstT>
-__global__ void __launch_bounds__(NT, MINB)
-resize_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned long long red[32];
-    const int tid = threadIdx.x;
-  const int frame = blockIdx.y;
-  const int clip = frame / A.T;
-  const int t = frame - clip * A.T;
-  const NexarClipParams* cp = A.params + clip;
-  const unsigned flags = cp->flags;
-  float scale;
-  if (A.pass == 0) {
-    scale = 1.0f / 255.0f;
-  } else {
-    const bool big = A.clip_max[clip] != 0u;
-    if (A.pass == 1 && big) return;
-    scale = big ? 1.0f / 255.0f : 1.0f;
-  }
-  const bool flip = flags & NEXAR_FLIP, aug = flags & NEXAR_AUG;
-  const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, flip);
-  const int nb = gridDim.x, band = blockIdx.x;
-  const int per = (B.i_hi - B.i_lo + nb - 1) / nb;
-  const int i0 = min(B.i_hi, B.i_lo + band * per), i1 = min(B.i_hi, i0 + per);
-  const int W3 = P.src_w * 3;
-  const int nchunks = W3 >> 4;
-  const int vstride = (W3 + KX * 3 + 15) & ~7;  // uint16 elements per staging buffer (16-byte multiple)
-  unsigned short* vb = (unsigned short*)smem_raw;
-  for (int e = W3 + tid; e < vstride; e += NT) vb[e] = vb[vstride + e] = 0;  // zero tail read by the padded taps
-
-  const int64_t dbase = (int64_t)clip * A.sb + (int64_t)t * A.st;
-  unsigned gsum = 0u;
-  unsigned orv = 0u;
-
-  if (i0 < i1) {
-    // ---- horizontal taps of this thread's output pixel (registers) ----
-    const int nj = B.j_hi - B.j_lo;
-    const bool hth = tid < nj;
-    const int j = B.j_lo + (hth ? tid : 0);
-    constexpr int NW = KX / 2;  // taps as dp2a operands (two 15-bit taps per word), in registers
-    unsigned wx[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) wx[k] = hth ? P.xw16[(size_t)j * NW + k] : 0u;
-    const unsigned hbyte = (unsigned)(P.xstart_al[j] * 3) * 2u;  // byte offset of the first tap in a staging row
-    int xo = j + B.ox;
-    if (flip) xo = P.cs - 1 - xo;
-    const float post = scale * (1.0f / (128.0f * 32768.0f));
-    // where this thread's pixel goes (row term added per output row): intermediate (augmented clips) or dst
-    char* const optr = aug ? (char*)(A.inter + ((int64_t)frame * A.bh - B.by0) * A.bw + (xo - B.bx0))
-                           : (char*)A.dst + (dbase + (int64_t)xo * A.sx) * (int64_t)sizeof(DstT);
-
-    // ---- vertical pass state ----
-    const unsigned rnd = 1u << 7;  // P.shift == 15: staging value = (acc + 128) >> 8
-    unsigned acc0[16], acc1[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) acc0[q] = acc1[q] = 0u;
-    const int p0 = P.ystart[i0] >> 1;
-    const int plast = (P.ystart[i1 - 1] + P.ycount[i1 - 1] - 1) >> 1;  // inclusive
-    const int chunk = min(tid, nchunks - 1);  // surplus threads shadow the last chunk (no divergence); they never stage
-    const bool vstore = tid < nchunks;
-    const char* frame_base = (const char*)A.src + A.frame_offsets[frame];
-    const unsigned rs = (unsigned)A.src_row_stride;
-    const unsigned vbytes = (unsigned)vstride * 2u;
-    unsigned bufoff = 0u;  // byte offset of the current staging buffer (uniform)
-    // ---- TMA pipeline: NS stages of one row pair each, filled by bulk copies issued by thread 0 ----
-    const unsigned stage_bytes = 2u * (unsigned)W3;
-    unsigned char* const stage0 = smem_raw + 2u * vbytes;
-    unsigned long long* const bars = (unsigned long long*)(stage0 + (unsigned)NS * stage_bytes);  // full[NS], empty[NS]
-    const unsigned bar_full = (unsigned)__cvta_generic_to_shared(bars), bar_empty = bar_full + 8u * NS;
-    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage0);
-    if (tid == 0) {
-      for (int s = 0; s < NS; ++s) {
-        mbar_init(bar_full + 8u * s, 1u);
-        mbar_init(bar_empty + 8u * s, (unsigned)(NT / 32));
-      }
-      mbar_fence_init();
-    }
-    __syncthreads();
-    const int n_pairs = plast - p0 + 1;
-    int issued = 0;  // thread 0 only: pairs whose copy has been issued
-    auto issue_pair = [&](int n) {
-      const unsigned s = (unsigned)n % NS;
-      const char* g = frame_base + (size_t)(2 * (p0 + n)) * rs;
-      mbar_expect_tx(bar_full + 8u * s, stage_bytes);
-      if (rs == (unsigned)W3) {
-        bulk_g2s(stage_s + s * stage_bytes, g, stage_bytes, bar_full + 8u * s);
-      } else {
-        bulk_g2s(stage_s + s * stage_bytes, g, (unsigned)W3, bar_full + 8u * s);
-        bulk_g2s(stage_s + s * stage_bytes + (unsigned)W3, g + rs, (unsigned)W3, bar_full + 8u * s);
-      }
-    };
-    if (tid == 0) {
-      for (; issued < min(NS, n_pairs); ++issued) issue_pair(issued);
-    }
-    const unsigned coff = (unsigned)chunk * 16u;
-    uint4 e_nx = __ldg(P.pairs + p0);
-
-#define NEXAR_ACCUM(ACC, WV)                                 \
-  {                                                          \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) {          \
-      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], ACC[4 * q + 0]); \
-      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], ACC[4 * q + 1]); \
-      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], ACC[4 * q + 2]); \
-      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], ACC[4 * q + 3]); \
-    }                                                        \
-  }
-#define NEXAR_ACCUM_BEGIN(ACC, WV)                  \
-  {                                                 \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) { \
-      ACC[4 * q + 0] = __dp2a_lo(WV, lo[q], rnd);   \
-      ACC[4 * q + 1] = __dp2a_hi(WV, lo[q], rnd);   \
-      ACC[4 * q + 2] = __dp2a_lo(WV, hi[q], rnd);   \
-      ACC[4 * q + 3] = __dp2a_hi(WV, hi[q], rnd);   \
-    }                                               \
-  }
-#define NEXAR_STAGE(ACC)                                                                      \
-  {                                                                                           \
-    unsigned w_[8];                                                                           \
-    _Pragma("unroll") for (int q = 0; q < 8; ++q)                                             \
-        w_[q] = __byte_perm(ACC[2 * q], ACC[2 * q + 1], 0x6521); /* (a >> 8) | (b >> 8) << 16 */ \
-    if (vstore) {                                                                             \
-      uint4* d_ = (uint4*)(smem_raw + bufoff + (unsigned)tid * 32u);                          \
-      d_[0] = make_uint4(w_[0], w_[1], w_[2], w_[3]);                                         \
-      d_[1] = make_uint4(w_[4], w_[5], w_[6], w_[7]);                                         \
-    }                                                                                         \
-  }
-// One row pair: CA/CB hold rows 2p / 2p+1 of this thread's chunk, NA/NB receive the next pair.
-#define NEXAR_PAIR()                                                                                       \
-  {                                                                                                        \
-    const int n = p - p0;                                                                                  \
-    const unsigned st = (unsigned)n % NS, par = ((unsigned)n / NS) & 1u;                                   \
-    if (tid == 0) { /* producer: refill every stage whose previous round has been released */            \
-      while (issued < n_pairs && issued < n + NS) {                                                        \
-        const unsigned s2 = (unsigned)issued % NS, r2 = (unsigned)issued / NS;                             \
-        if (r2 > 0u && !mbar_test(bar_empty + 8u * s2, (r2 - 1u) & 1u)) break;                             \
-        issue_pair(issued);                                                                                \
-        ++issued;                                                                                          \
-      }                                                                                                    \
-    }                                                                                                      \
-    mbar_wait(bar_full + 8u * st, par);                                                                    \
-    const uint4 CA = *(const uint4*)(stage0 + st * stage_bytes + coff);                                    \
-    const uint4 CB = *(const uint4*)(stage0 + st * stage_bytes + (unsigned)W3 + coff);                     \
-    const unsigned ex = e_nx.x, ey = e_nx.y, ez = e_nx.z;                                                  \
-    e_nx = __ldg(P.pairs + min(p + 1, plast)); /* control words of the next pair, one iteration ahead */   \
-    orv |= (CA.x | CA.y) | (CA.z | CA.w) | (CB.x | CB.y) | (CB.z | CB.w);                                  \
-    unsigned lo[4], hi[4];                                                                                 \
-    lo[0] = __byte_perm(CA.x, CB.x, 0x5140); hi[0] = __byte_perm(CA.x, CB.x, 0x7362);                      \
-    lo[1] = __byte_perm(CA.y, CB.y, 0x5140); hi[1] = __byte_perm(CA.y, CB.y, 0x7362);                      \
-    lo[2] = __byte_perm(CA.z, CB.z, 0x5140); hi[2] = __byte_perm(CA.z, CB.z, 0x7362);                      \
-    lo[3] = __byte_perm(CA.w, CB.w, 0x5140); hi[3] = __byte_perm(CA.w, CB.w, 0x7362);                      \
-    __syncwarp();                                                                                          \
-    if ((tid & 31) == 0) mbar_arrive(bar_empty + 8u * st); /* this warp is done with the stage */          \
-    if ((ez & 0xFu) == 0u) { /* common case: no row starts or ends in this pair */                                \
-      if (ex) NEXAR_ACCUM(acc0, ex)                                                                      \
-      if (ey) NEXAR_ACCUM(acc1, ey)                                                                      \
-    } else {                                                                                               \
-      if (ex) {                                                                                           \
-        if (ez & NEXAR_E_BEGIN0) NEXAR_ACCUM_BEGIN(acc0, ex) else NEXAR_ACCUM(acc0, ex)                 \
-      }                                                                                                    \
-      if (ey) {                                                                                           \
-        if (ez & NEXAR_E_BEGIN1) NEXAR_ACCUM_BEGIN(acc1, ey) else NEXAR_ACCUM(acc1, ey)                 \
-      }                                                                                                    \
-    }                                                                                                      \
-    if (ez & NEXAR_E_EMIT) { /* an output row finished with this pair */                                  \
-      const int row = (int)((ez >> NEXAR_E_ROWSHIFT) & 0xFFFu);                                                      \
-      const bool s1 = (ez & NEXAR_E_SLOT) != 0u;                                                          \
-      if (row >= i0 && row < i1) {                                                                         \
-        if (s1) NEXAR_STAGE(acc1) else NEXAR_STAGE(acc0)                                                   \
-        __syncthreads();                                                                                   \
-        if (hth) {                                                                                         \
-          const unsigned* src = (const unsigned*)(smem_raw + bufoff + hbyte);                              \
-          unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
-          _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
-            const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
-            const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
-                           bb = __byte_perm(w1, w2, 0x7610);                                               \
-            rl = __dp2a_lo(rr, wx[m], rl); rh = __dp2a_hi(rr, wx[m], rh);                                  \
-            gl = __dp2a_lo(gg, wx[m], gl); gh = __dp2a_hi(gg, wx[m], gh);                                  \
-            bl_ = __dp2a_lo(bb, wx[m], bl_); bh = __dp2a_hi(bb, wx[m], bh);                                \
-          }                                                                                                \
-          float r = (float)(int)(rh * 256u + rl) * post;                                                   \
-          float g = (float)(int)(gh * 256u + gl) * post;                                                   \
-          float bl = (float)(int)(bh * 256u + bl_) * post;                                                 \
-          const int y = row + B.oy;                                                                        \
-          if (aug) {                                                                                       \
-            const float bright = cp->brightness;                                                           \
-            r = clamp01(__fmul_rn(bright, r));                                                             \
-            g = clamp01(__fmul_rn(bright, g));                                                             \
-            bl = clamp01(__fmul_rn(bright, bl));                                                           \
-            gsum += gray_fix(r, g, bl);                                                                     \
-            ((float4*)optr)[(int64_t)y * A.bw] = make_float4(r, g, bl, 0.0f);                              \
-          } else {                                                                                         \
-            DstT* const o = (DstT*)optr + (int64_t)y * A.sy;                                               \
-            if (A.normalize) {                                                                             \
-              r = fmaf(r, A.nscale[0], A.nbias[0]);                                                        \
-              g = fmaf(g, A.nscale[1], A.nbias[1]);                                                        \
-              bl = fmaf(bl, A.nscale[2], A.nbias[2]);                                                      \
-            }                                                                                              \
-            store_out<DstT>(o, 0, r);                                                                      \
-            store_out<DstT>(o, A.sc, g);                                                                   \
-            store_out<DstT>(o, 2 * A.sc, bl);                                                              \
-          }                                                                                                \
-        }                                                                                                  \
-        bufoff = vbytes - bufoff; /* other staging buffer */                                               \
-      }                                                                                                    \
-      const unsigned wpost = ez & 0xFFFF0000u;                                                             \
-      if (wpost) { /* first tap of the slot's next row shares this pair */                                 \
-        if (s1) NEXAR_ACCUM_BEGIN(acc1, wpost) else NEXAR_ACCUM_BEGIN(acc0, wpost)                         \
-      }                                                                                                    \
-    }                                                                                                      \
-  }
-
-    for (int p = p0; p <= plast; ++p) NEXAR_PAIR()
-#undef NEXAR_PAIR
-#undef NEXAR_ACCUM
-#undef NEXAR_ACCUM_BEGIN
-#undef NEXAR_STAGE
-  }
-
-  if (!aug) fill_pads<DstT, NT>(P, A, B, dbase, band, nb, i0, i1, tid);
-  if (A.pass == 0) {
-    const bool big = (orv & 0xFEFEFEFEu) != 0u;
-    if (__any_sync(0xffffffffu, big) && (tid & 31) == 0) atomicOr(&A.clip_max[clip], 1u);
-  }
-  if (aug) {
-    const unsigned long long s = block_sum((unsigned long long)gsum, red);
-    if (tid == 0) A.gray_partial[((size_t)(scale == 1.0f) * A.n_frames + frame) * kMaxBands + band] = s;
+  if constexpr (FUSED) {
+    // aug is a property of the clip, hence uniform over the cluster: either every CTA of it takes the barriers or none
+    if (aug) fused_colour_geometry<DstT, NT, true>(P, A, cp, flags, frame, clip, t, band, nb, B, i0, i1, 0);
   }
 }
 
 // ---------------------------------------------------------------------------------
 // colour chain on one pixel: contrast -> saturation -> hue  (tv:_functional_tensor.py:181-321)
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void hue_shift(float& r, float& g, float& b, float hue) {
-  // tv _rgb2hsv -> (h + hue) % 1 -> _hsv2rgb.  Divisions go through the fast reciprocal: the result
-  // feeds a 1e-3 gate, and every branch of the hexcone is continuous at its boundaries.
-  const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
-  const bool eqc = maxc == minc;
-  const float cr = maxc - minc;
-  const float s = __fdividef(cr, eqc ? 1.0f : maxc);
-  const float inv = __fdividef(1.0f, eqc ? 1.0f : cr);
-  const float rc = (maxc - r) * inv, gc = (maxc - g) * inv, bc = (maxc - b) * inv;
-  float h = (maxc == r) ? (bc - gc) : (maxc == g) ? (2.0f + rc - bc) : (4.0f + gc - rc);
-  h = h * (1.0f / 6.0f) + 1.0f;
-  h -= floorf(h);                       // fmod(h/6 + 1, 1)
-  float hh = h + hue;
-  hh -= floorf(hh);                     // python-style (h + hue) % 1.0
-  const float v = maxc;
-  const float h6 = hh * 6.0f;
-  const float fi = floorf(h6);
-  const float f = h6 - fi;
-  int i = (int)fi;
-  i = i >= 6 ? i - 6 : i;
-  const float p = clamp01(v * (1.0f - s));
-  const float q = clamp01(v * (1.0f - s * f));
-  const float tt = clamp01(v * (1.0f - s * (1.0f - f)));
-  r = (i == 0 || i == 5) ? v : (i == 1) ? q : (i == 4) ? tt : p;
-  g = (i == 1 || i == 2) ? v : (i == 0) ? tt : (i == 3) ? q : p;
-  b = (i == 3 || i == 4) ? v : (i == 2) ? tt : (i == 5) ? q : p;
-}
-
 struct ColourParams {
-  float cmean, contrast, saturation, saturation_q, hue;  // cmean = contrast_q * frame mean
+  float cmean, contrast, saturation, saturation_q, hue6;  // cmean = contrast_q * frame mean; hue6 = 6 * hue factor
 };
+// torchvision's formulas written for the instruction count: multiply-adds are contracted (1 ulp against tv's separately
+// rounded _blend), and the hue rotation works in sextant units without the HSV detour:
+//   H = (h6 + 6 * hue) mod 6 with h6 torchvision's un-normalised hue, and for every channel
+//   out = minc + cr * f(H),  f_r = sat(|H - 3| - 1), f_g = sat(2 - |H - 2|), f_b = sat(2 - |H - 4|)
+// which is _hsv2rgb's (v, q, p, p, t, v) table with v * s = cr = maxc - minc (tv:_functional_tensor.py:258-321).
+// hue == 0: torchvision still runs RGB -> HSV -> RGB, which is the identity up to a few ulp; it is skipped (uniform per
+// frame).  Measured against the oracle, which always runs it: < 1e-6.
 __device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const ColourParams& c) {
-  // tv _blend: (ratio * img + (1 - ratio) * other).clamp(0, 1)
-  r = clamp01(__fadd_rn(__fmul_rn(c.contrast, r), c.cmean));
-  g = clamp01(__fadd_rn(__fmul_rn(c.contrast, g), c.cmean));
-  b = clamp01(__fadd_rn(__fmul_rn(c.contrast, b), c.cmean));
-  const float gq = __fmul_rn(c.saturation_q, gray_of(r, g, b));
-  r = clamp01(__fadd_rn(__fmul_rn(c.saturation, r), gq));
-  g = clamp01(__fadd_rn(__fmul_rn(c.saturation, g), gq));
-  b = clamp01(__fadd_rn(__fmul_rn(c.saturation, b), gq));
-  // hue == 0: torchvision still runs RGB -> HSV -> RGB, which is the identity up to a few ulp (p = v - (max - min) etc.);
-  // the round trip is skipped here (uniform per frame).  Measured against the oracle, which always runs it: < 1e-6.
-  if (c.hue != 0.0f) hue_shift(r, g, b, c.hue);
+  r = __saturatef(fmaf(c.contrast, r, c.cmean));
+  g = __saturatef(fmaf(c.contrast, g, c.cmean));
+  b = __saturatef(fmaf(c.contrast, b, c.cmean));
+  const float gq = c.saturation_q * fmaf(0.114f, b, fmaf(0.587f, g, 0.2989f * r));
+  r = __saturatef(fmaf(c.saturation, r, gq));
+  g = __saturatef(fmaf(c.saturation, g, gq));
+  b = __saturatef(fmaf(c.saturation, b, gq));
+  if (c.hue6 != 0.0f) {
+    const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+    const float cr = maxc - minc;
+    const float inv = cr > 0.0f ? __fdividef(1.0f, cr) : 0.0f;
+    const float mi = maxc * inv;
+    const float rc = fmaf(-r, inv, mi), gc = fmaf(-g, inv, mi), bc = fmaf(-b, inv, mi);
+    const float h6 = (maxc == r) ? (bc - gc) : (maxc == g) ? (2.0f + rc - bc) : (4.0f + gc - rc);
+    float H = h6 + c.hue6;                     // in (-7, 11): fold into [0, 6)
+    H -= 6.0f * floorf(H * (1.0f / 6.0f));
+    r = fmaf(cr, __saturatef(fabsf(H - 3.0f) - 1.0f), minc);
+    g = fmaf(cr, __saturatef(2.0f - fabsf(H - 2.0f)), minc);
+    b = fmaf(cr, __saturatef(2.0f - fabsf(H - 4.0f)), minc);
+  }
 }
 
 __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, int frame, int slot, int nbands) {
@@ -1374,7 +1165,8 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant_
   FrameInfo fi;
   fi.flags = cp->flags;
   fi.reserved = 0;
-  if (!(fi.flags & NEXAR_AUG)) {
+  // A.pass == 4: fixup_frame_kernel finishes the clips whose maximum was <= 1 on its own; K2 / K3 skip them
+  if (!(fi.flags & NEXAR_AUG) || (A.pass == 4 && A.clip_max[clip] == 0u)) {
     A.finfo[frame].flags = 0u;
     return;
   }
@@ -1384,7 +1176,7 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant_
   c.contrast = cp->contrast;
   c.saturation = cp->saturation;
   c.saturation_q = cp->saturation_q;
-  c.hue = cp->hue;
+  c.hue6 = 6.0f * cp->hue;
   float r = 0.0f, g = 0.0f, b = 0.0f;
   colour_chain(r, g, b, c);
   const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, fi.flags & NEXAR_FLIP);
@@ -1392,14 +1184,13 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant_
   fi.by0 = B.by0; fi.by1 = B.by1; fi.bx0 = B.bx0; fi.bx1 = B.bx1;
 #pragma unroll
   for (int k = 0; k < 6; ++k) fi.grid[k] = cp->grid[k];
-  fi.contrast = c.contrast; fi.saturation = c.saturation; fi.saturation_q = c.saturation_q; fi.hue = c.hue;
+  fi.contrast = c.contrast; fi.saturation = c.saturation; fi.saturation_q = c.saturation_q; fi.hue = c.hue6;
   A.finfo[frame] = fi;
 }
 
 // K2: contrast/saturation/hue in place on the frame's content box (which always fills the
-// [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them).
-// The result is stored RELATIVE to the pad colour, so that K3 can treat pad neighbours as zeros.
-constexpr int kColourPerThread = 4;
+// [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them), 8-byte q15 pixels.
+constexpr int kColourPerThread = 8;
 #ifndef NEXAR_COL_MINB
 #define NEXAR_COL_MINB 6
 #endif
@@ -1408,29 +1199,28 @@ __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __gri
   // K3 then starts with frame 0, which this kernel wrote last)
   const int frame = (int)(gridDim.y - 1u - blockIdx.y);
   const float4* fi4 = (const float4*)(A.finfo + frame);
-  const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, hue, -
+  const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, 6 * hue, -
   if (!(__float_as_uint(q3.z) & NEXAR_AUG)) return;
   ColourParams c;
   c.cmean = st.w;
   c.contrast = q3.w;
   c.saturation = q4.x;
   c.saturation_q = q4.y;
-  c.hue = q4.z;
+  c.hue6 = q4.z;
   const int n = A.bh * A.bw;
-  float4* base = A.inter + (size_t)frame * n;
+  uint2* base = A.inter + (size_t)frame * n;
   const int i0 = blockIdx.x * (256 * kColourPerThread) + threadIdx.x;
-  float4 v[kColourPerThread];
+  uint2 v[kColourPerThread];
 #pragma unroll
   for (int k = 0; k < kColourPerThread; ++k)
     if (i0 + k * 256 < n) v[k] = base[i0 + k * 256];
 #pragma unroll
   for (int k = 0; k < kColourPerThread; ++k)
     if (i0 + k * 256 < n) {
-      colour_chain(v[k].x, v[k].y, v[k].z, c);
-      v[k].x -= st.x;
-      v[k].y -= st.y;
-      v[k].z -= st.z;
-      base[i0 + k * 256] = v[k];
+      float r, g, b;
+      unpack_q21(v[k], r, g, b);
+      colour_chain(r, g, b, c);
+      base[i0 + k * 256] = pack_q15(r, g, b);
     }
 }
 
@@ -1476,30 +1266,329 @@ __device__ __forceinline__ void point_effects(float& r, float& g, float& b, cons
   }
 }
 
-// Every frame of a clip shares the clip's affine map, content box and flags, so the per-pixel geometry (source
-// position, the four neighbour offsets, their weights and the interpolated ones-mask) is computed ONCE and reused
-// for kGeoFrames consecutive frames of the clip; per frame only the pad colour changes.  Thread block = 32 x
-// (8 * kGeoRows) output pixels x kGeoFrames frames; a warp owns a strip of 32 x kGeoRows pixels (consecutive rows,
-// one pixel per thread and row).  The strip is classified once, by every lane identically (no shared memory, no
-// barrier), from the image of its centre and the half extents of an affine map: FILL — maps strictly inside the
-// canvas and entirely into the pad band beside the content: constant pad colour, no memory traffic; INTERIOR — every
-// bilinear neighbour is a content pixel (weights as they are, mask 1); otherwise the four addresses are clamped into
-// the content box and the weights of neighbours that are pad or outside the canvas are zeroed (the intermediate is
-// stored relative to the pad colour, so pad neighbours contribute through the mask only).  All three classes and the
-// no-affine case then run the same per-frame code: out = m * (pad * m + sum(v * w)).
+enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
+constexpr unsigned kTailFlags = NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT;
+
+// ---------------------------------------------------------------------------------
+// Fused tail of resize_fast_kernel<..., FUSED = true>: K2 + K3 of one frame inside the cluster that resized it.
+//   phase B  every CTA runs contrast -> saturation -> hue in place on the rows of the intermediate its own band wrote
+//            (needs the frame's gray mean: the band sums are exchanged through global memory and the first cluster barrier);
+//   phase C  after the second cluster barrier every CTA produces a share of the OUTPUT rows (groups of four rows dealt round
+//            robin, so that pad and content rows are spread evenly): a warp owns 16 x 4 output pixels, two horizontally
+//            adjacent pixels per lane (one 32-bit bf16x2 / 64-bit float2 store per channel), classified FILL / INTERIOR /
+//            general exactly like geometry_kernel; the four neighbours are 8-byte loads of the q15 intermediate (L2 / L1
+//            hits: the cluster wrote them microseconds ago), unpacked with one PRMT per sample:
+//              sum_canvas(w * img) = pad * (m - wc) + k * sum_content(w * F) - k * wc,   F = 1 + q / 32768, k = 32768 / 32767
+//            with m the interpolated ones-mask and wc the total weight of the content neighbours; out = m * that (tv fill = 0).
+// ---------------------------------------------------------------------------------
+struct GeoPx {
+  int o00, o01, o10, o11;                     // pixel offsets from the frame's canvas origin
+  float w00, w01, w10, w11, m, wc;
+};
+constexpr int kMaxTileClasses = 1536;         // tiles per CTA whose class is kept in shared memory (more are classified on the fly)
+
+// grayscale / noise of the augmentation tail (rare: kept out of line)
+__device__ __noinline__ float3 tail_pre_effects(float r, float g, float b, const NexarClipParams* cp, unsigned flags, int frame,
+                                                int idx, int cs) {
+  if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+  if (flags & NEXAR_NOISE) {
+    const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
+    r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+    g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
+    b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+  }
+  return make_float3(r, g, b);
+}
+__device__ __noinline__ float3 tail_point_effects(float r, float g, float b, const NexarClipParams* cp, unsigned flags, int y, int x) {
+  point_effects(r, g, b, cp, flags, y, x);
+  return make_float3(r, g, b);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_pair(T* p, float a, float b);
+template <>
+__device__ __forceinline__ void store_pair<float>(float* p, float a, float b) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+template <>
+__device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(*(const unsigned*)&h) : "memory");
+}
+
+template <typename DstT, int NT, bool CLUSTER>
+__device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KArgs& A, const NexarClipParams* cp,
+                                                      unsigned flags, int frame, int clip, int t, int band, int nb,
+                                                      const Box& B, int i0, int i1, int slot) {
+  __shared__ float fconst[4];  // pad colour after the colour chain, contrast_q * gray mean
+  __shared__ unsigned char tile_cls[kMaxTileClasses];
+  __shared__ int tile_next[1];
+  const int tid = threadIdx.x;
+  // CLUSTER: the nb bands of the frame are the CTAs of one cluster; otherwise one CTA owns the whole frame (nb == 1)
+  auto sync_all = [&]() {
+    if (CLUSTER) cluster_sync_all();
+    else { __threadfence_block(); __syncthreads(); }
+  };
+  sync_all();                  // every band's gray sum is in global memory
+  ColourParams c;
+  c.contrast = cp->contrast; c.saturation = cp->saturation; c.saturation_q = cp->saturation_q; c.hue6 = 6.0f * cp->hue;
+  if (tid == 0) {
+    c.cmean = __fmul_rn(cp->contrast_q, frame_mean(A, P, frame, slot, nb));
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    colour_chain(r, g, b, c);
+    fconst[0] = r; fconst[1] = g; fconst[2] = b; fconst[3] = c.cmean;
+  }
+  __syncthreads();
+  const float padr = fconst[0], padg = fconst[1], padb = fconst[2];
+  c.cmean = fconst[3];
+  // ---- phase B: colour chain in place on this band's rows -------------------------------------------------------
+  if (!(NEXAR_EXP & 1)) {
+    const int nrows = i1 - i0, bwid = B.bx1 - B.bx0;
+    uint2* const rows = A.inter + ((int64_t)frame * A.bh + (i0 + B.oy - B.by0)) * A.bw;
+    if (bwid == A.bw) {  // the content box fills the allocation (always, for a letterbox): one flat, coalesced sweep
+      const int n = nrows * A.bw;
+      constexpr int U = 4;
+      for (int e0 = tid; e0 < n; e0 += U * NT) {
+        uint2 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          if (e0 + k * NT < n) v[k] = rows[e0 + k * NT];
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          if (e0 + k * NT < n) {
+            float r, g, b;
+            unpack_q21(v[k], r, g, b);
+            colour_chain(r, g, b, c);
+            rows[e0 + k * NT] = pack_q15(r, g, b);
+          }
+      }
+    } else {
+      for (int row = tid >> 5; row < nrows; row += NT / 32)
+        for (int col = tid & 31; col < bwid; col += 32) {
+          uint2* q = rows + row * A.bw + col;
+          const uint2 v = *q;
+          float r, g, b;
+          unpack_q21(v, r, g, b);
+          colour_chain(r, g, b, c);
+          *q = pack_q15(r, g, b);
+        }
+    }
+  }
+  // ---- tile classes of phase C (geometry only: done before the barrier so that it overlaps the wait) -------------------
+  const int ngroups = (P.cs + 3) >> 2, tiles_x = (P.cs + 31) >> 5;
+  const int ntiles = (band < ngroups ? (ngroups - band + nb - 1) / nb : 0) * tiles_x;
+  auto classify = [&](int tx, int ty0) -> int {
+    if (!(flags & NEXAR_AFFINE)) return GEO_GENERAL;
+    const float fcs = (float)P.cs, half = 0.5f * fcs;
+    const float g0 = cp->grid[0], g1 = cp->grid[1], g2 = cp->grid[2], g3 = cp->grid[3], g4 = cp->grid[4], g5 = cp->grid[5];
+    // image of the tile centre +- the half extents of the tile under the linear part (a superset for tiles that stick
+    // out of the canvas); 0.01 px of slack for rounding differences against the per-pixel evaluation
+    const float ex = (15.5f * fabsf(g0) + 1.5f * fabsf(g1)) * half + 0.01f;
+    const float ey = (15.5f * fabsf(g3) + 1.5f * fabsf(g4)) * half + 0.01f;
+    const float xc = (float)(tx * 32 + 16) - half, yc = (float)(ty0 + 2) - half;
+    const float sxc = fmaf(fmaf(yc, g1, xc * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float syc = fmaf(fmaf(yc, g4, xc * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float xmin = sxc - ex, xmax = sxc + ex, ymin = syc - ey, ymax = syc + ey;
+    const float fby0 = (float)B.by0, fby1 = (float)B.by1, fbx0 = (float)B.bx0, fbx1 = (float)B.bx1;
+    const bool inside = xmin >= 0.0f && xmax <= fcs - 1.0f && ymin >= 0.0f && ymax <= fcs - 1.0f;
+    const bool outside_box = ymax + 1.0f < fby0 || ymin >= fby1 || xmax + 1.0f < fbx0 || xmin >= fbx1;
+    const bool interior = xmin >= fbx0 && xmax <= fbx1 - 1.0f && ymin >= fby0 && ymax <= fby1 - 1.0f;
+    return (inside && outside_box) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
+  };
+  for (int tile = tid; tile < min(ntiles, kMaxTileClasses); tile += NT) {
+    const int gk = tile / tiles_x, tx = tile - gk * tiles_x;
+    tile_cls[tile] = (unsigned char)classify(tx, (band + gk * nb) * 4);
+  }
+  if (tid == 0) *tile_next = 0;
+  sync_all();                  // the whole frame is colour-adjusted
+  // ---- phase C: affine gather + effects + normalise + store -------------------------------------------------------
+  // Warp tile = 32 x 4 output pixels: lane -> (x pair = lane & 15, row = lane >> 4), two passes two rows apart.  The CTA's
+  // tiles (its row groups x the tile columns) were classified once, into shared memory, before the barrier above; the
+  // warps then pull tiles from a shared counter (FILL tiles cost a few stores, general ones about 700 instructions).
+  const int cs = P.cs;
+  const int lane = tid & 31;
+  const float half = (float)cs * 0.5f, fcs = (float)cs;
+  const bool affine = (flags & NEXAR_AFFINE) != 0u;
+  const float g0 = cp->grid[0], g1 = cp->grid[1], g2 = cp->grid[2], g3 = cp->grid[3], g4 = cp->grid[4], g5 = cp->grid[5];
+  const int bw = A.bw;
+  const uint2* const fr = A.inter + ((int64_t)frame * (A.bh * bw) - (B.by0 * bw + B.bx0));  // indexed by canvas (y, x)
+  DstT* const ob = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t * A.st);
+  const int osy = (int)A.sy, osc = (int)A.sc, osx = (int)A.sx;
+  const bool vec2 = A.sx == 1 && ((A.sy | A.sc | A.sb | A.st) & 1) == 0 && (((uintptr_t)A.dst) & (2 * sizeof(DstT) - 1)) == 0;
+  const bool tail_fx = (flags & kTailFlags) != 0u;
+  const int lx = (lane & 15) * 2, ly = lane >> 4;
+  const float nsr = A.nscale[0], nsg = A.nscale[1], nsb = A.nscale[2], nbr = A.nbias[0], nbg = A.nbias[1], nbb = A.nbias[2];
+
+  auto geo = [&](GeoPx& q, float xg0, float xg3, float yb, int x, int y, int cls) {
+    q.m = 1.0f;
+    if (affine) {
+      // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
+      const float gx = fmaf(yb, g1, xg0) + g2;
+      const float gy = fmaf(yb, g4, xg3) + g5;
+      const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
+      const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const float wx1 = ix - x0f, wy1 = iy - y0f;
+      const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+      if (cls == GEO_INTERIOR) {
+        q.o00 = (int)y0f * bw + (int)x0f;   // the other three neighbours sit at +1, +bw, +bw+1
+        q.w00 = wx0 * wy0; q.w01 = wx1 * wy0; q.w10 = wx0 * wy1; q.w11 = wx1 * wy1;
+        q.wc = 1.0f;
+      } else {
+        // clamp before the int cast so wild matrices cannot overflow
+        const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
+        const int yq = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
+        const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
+        const bool iny0 = (unsigned)yq < (unsigned)cs, iny1 = (unsigned)(yq + 1) < (unsigned)cs;
+        const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
+        q.m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
+        const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
+        const bool cy0 = yq >= B.by0 && yq < B.by1, cy1 = yq + 1 >= B.by0 && yq + 1 < B.by1;
+        const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
+        const int xc0 = min(max(x0, B.bx0), B.bx1 - 1), xc1 = min(max(x0 + 1, B.bx0), B.bx1 - 1);
+        const int yc0 = min(max(yq, B.by0), B.by1 - 1) * bw, yc1 = min(max(yq + 1, B.by0), B.by1 - 1) * bw;
+        q.o00 = yc0 + xc0; q.o01 = yc0 + xc1; q.o10 = yc1 + xc0; q.o11 = yc1 + xc1;
+        q.w00 = bx0w * by0w; q.w01 = bx1w * by0w; q.w10 = bx0w * by1w; q.w11 = bx1w * by1w;
+        q.wc = (bx0w + bx1w) * (by0w + by1w);
+      }
+    } else {
+      // no affine: the pixel itself when it is content, the pad colour otherwise
+      const bool in = y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1;
+      q.o00 = q.o01 = q.o10 = q.o11 = min(max(y, B.by0), B.by1 - 1) * bw + min(max(x, B.bx0), B.bx1 - 1);
+      q.w00 = q.wc = in ? 1.0f : 0.0f;
+      q.w01 = q.w10 = q.w11 = 0.0f;
+    }
+  };
+  auto gather = [&](const GeoPx& q, int cls, uint2& v00, uint2& v01, uint2& v10, uint2& v11) {
+    if (cls == GEO_INTERIOR) {  // one address, immediate offsets
+      const uint2* p0 = fr + q.o00;
+      const uint2* p1 = p0 + bw;
+      v00 = p0[0]; v01 = p0[1]; v10 = p1[0]; v11 = p1[1];
+    } else {
+      v00 = fr[q.o00]; v01 = fr[q.o01]; v10 = fr[q.o10]; v11 = fr[q.o11];
+    }
+  };
+  auto blend = [&](const GeoPx& q, const uint2& v00, const uint2& v01, const uint2& v10, const uint2& v11, int cls, float& r,
+                   float& g, float& b) {
+    const float sr = fmaf(q15_r(v11), q.w11, fmaf(q15_r(v10), q.w10, fmaf(q15_r(v01), q.w01, q15_r(v00) * q.w00)));
+    const float sg = fmaf(q15_g(v11), q.w11, fmaf(q15_g(v10), q.w10, fmaf(q15_g(v01), q.w01, q15_g(v00) * q.w00)));
+    const float sb = fmaf(q15_b(v11), q.w11, fmaf(q15_b(v10), q.w10, fmaf(q15_b(v01), q.w01, q15_b(v00) * q.w00)));
+    if (cls == GEO_INTERIOR) {  // m = wc = 1
+      r = fmaf(sr, kQ15Inv, -kQ15Inv);
+      g = fmaf(sg, kQ15Inv, -kQ15Inv);
+      b = fmaf(sb, kQ15Inv, -kQ15Inv);
+    } else {
+      const float t0 = -kQ15Inv * q.wc, pm = q.m - q.wc;
+      r = q.m * fmaf(sr, kQ15Inv, fmaf(padr, pm, t0));
+      g = q.m * fmaf(sg, kQ15Inv, fmaf(padg, pm, t0));
+      b = q.m * fmaf(sb, kQ15Inv, fmaf(padb, pm, t0));
+    }
+  };
+
+#pragma unroll 1
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(tile_next, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ((NEXAR_EXP & 2) ? 0 : ntiles)) break;
+    const int gk = tile / tiles_x, tx = tile - gk * tiles_x;
+    const int ty0 = (band + gk * nb) * 4;
+    const int cls = tile < kMaxTileClasses ? (int)tile_cls[tile] : classify(tx, ty0);
+    const int x = tx * 32 + lx;
+    const bool has2 = x + 1 < cs;
+    const float xb = (float)x - half + 0.5f;
+    const float xg0a = xb * g0, xg3a = xb * g3, xg0b = (xb + 1.0f) * g0, xg3b = (xb + 1.0f) * g3;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int y = ty0 + ly + 2 * pass;
+      if (y >= cs || x >= cs) break;  // lanes past the canvas idle until the warp pulls its next tile
+      float ra = padr, ga = padg, ba = padb, rb = padr, gb = padg, bb = padb;
+      if (cls != GEO_FILL) {
+        const float yb = (float)y - half + 0.5f;
+        GeoPx qa, qb;
+        geo(qa, xg0a, xg3a, yb, x, y, cls);
+        geo(qb, has2 ? xg0b : xg0a, has2 ? xg3b : xg3a, yb, has2 ? x + 1 : x, y, cls);
+        uint2 a00, a01, a10, a11, b00, b01, b10, b11;
+        gather(qa, cls, a00, a01, a10, a11);
+        gather(qb, cls, b00, b01, b10, b11);
+        blend(qa, a00, a01, a10, a11, cls, ra, ga, ba);
+        blend(qb, b00, b01, b10, b11, cls, rb, gb, bb);
+      }
+      if (tail_fx) {
+        const int idx = y * cs + x;
+        float3 pa = tail_pre_effects(ra, ga, ba, cp, flags, frame, idx, cs);
+        float3 pb = has2 ? tail_pre_effects(rb, gb, bb, cp, flags, frame, idx + 1, cs) : pa;
+        if (flags & NEXAR_BLUR) {  // the blur kernel finishes the chain from the planar canvas
+          float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+          cv[idx] = pa.x; cv[cs * cs + idx] = pa.y; cv[2 * cs * cs + idx] = pa.z;
+          if (has2) { cv[idx + 1] = pb.x; cv[cs * cs + idx + 1] = pb.y; cv[2 * cs * cs + idx + 1] = pb.z; }
+          continue;
+        }
+        pa = tail_point_effects(pa.x, pa.y, pa.z, cp, flags, y, x);
+        if (has2) pb = tail_point_effects(pb.x, pb.y, pb.z, cp, flags, y, x + 1);
+        ra = pa.x; ga = pa.y; ba = pa.z; rb = pb.x; gb = pb.y; bb = pb.z;
+      }
+      // nscale / nbias are 1 / 0 when the output is not normalised
+      ra = fmaf(ra, nsr, nbr); rb = fmaf(rb, nsr, nbr);
+      ga = fmaf(ga, nsg, nbg); gb = fmaf(gb, nsg, nbg);
+      ba = fmaf(ba, nsb, nbb); bb = fmaf(bb, nsb, nbb);
+      const int off = y * osy + x * osx;
+      if (vec2 && has2) {
+        store_pair<DstT>(ob + off, ra, rb);
+        store_pair<DstT>(ob + (off + osc), ga, gb);
+        store_pair<DstT>(ob + (off + 2 * osc), ba, bb);
+      } else {
+        store_out_global<DstT>(ob + off, ra);
+        store_out_global<DstT>(ob + (off + osc), ga);
+        store_out_global<DstT>(ob + (off + 2 * osc), ba);
+        if (has2) {
+          store_out_global<DstT>(ob + (off + osx), rb);
+          store_out_global<DstT>(ob + (off + osx + osc), gb);
+          store_out_global<DstT>(ob + (off + osx + 2 * osc), bb);
+        }
+      }
+    }
+  }
+}
+
+// Second pass of the fast path: the clips whose maximum was <= 1 are NOT divided by 255 (nexar_video_aug.py:814).  Rare, so
+// it is ONE launch of one CTA per frame that exits at once for every other clip: the general fp32 resample of the whole
+// frame (values in [0,1] are below the resolution of the fixed-point staging) and, for augmented clips, the fused tail.
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256) fixup_frame_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  extern __shared__ float vbuf[];  // [src_w*3]
+  __shared__ unsigned long long red[32];
+  const int frame = blockIdx.x;
+  const int clip = frame / A.T;
+  if (A.clip_max[clip] != 0u) return;
+  resize_general_body<SrcT, DstT>(P, A, frame, 0, 1, vbuf, red);  // A.pass == 1: unscaled, gray sum in slot 1
+  const NexarClipParams* cp = A.params + clip;
+  const unsigned flags = cp->flags;
+  if (flags & NEXAR_AUG) {
+    const Box B = clip_box(P, cp->crop_dy, cp->crop_dx, (flags & NEXAR_FLIP) != 0u);
+    fused_colour_geometry<DstT, 256, false>(P, A, cp, flags, frame, clip, frame - clip * A.T, 0, 1, B, B.i_lo, B.i_hi, 1);
+  }
+}
+
+// K3.  Every frame of a clip shares the clip's affine map, content box and flags, so the per-pixel geometry (source
+// position, the four neighbour offsets, their weights, the interpolated ones-mask m and the content weight wc) is
+// computed ONCE and reused for kGeoFrames consecutive frames of the clip; per frame only the pad colour changes.
+// CTA = 8 warps, a warp owns a tile of 32 x 4 output pixels (lane -> x pair = lane & 15, row = lane >> 4, two passes two
+// rows apart) x kGeoFrames frames: two horizontally adjacent pixels per lane, so every channel goes out as one 32-bit
+// bf16x2 / 64-bit float2 store.  The tile is classified once, by every lane identically, from the image of its centre
+// and the half extents of the affine map: FILL — maps strictly inside the canvas and entirely into the pad band beside
+// the content: constant pad colour, no loads; INTERIOR — every bilinear neighbour is a content pixel (one address,
+// weights as they are, m = wc = 1); otherwise the four addresses are clamped into the content box and the weights of
+// neighbours that are pad or outside the canvas are zeroed.  The neighbours are 8-byte q15 pixels, one PRMT per sample:
+//   sum_canvas(w * img) = pad * (m - wc) + k * sum_content(w * F) - k * wc,   F = 1 + q / 32768, k = 32768 / 32767
+// and out = m * that (torchvision's fill = 0 multiplies the zero-padded sample by the interpolated mask once more).
 // Offsets inside one clip of the intermediate and one frame of the destination are 32-bit (checked on the host).
-#ifndef NEXAR_GEO_ROWS
-#define NEXAR_GEO_ROWS 4
-#endif
 #ifndef NEXAR_GEO_FRAMES
 #define NEXAR_GEO_FRAMES 4
 #endif
-constexpr int kGeoRows = NEXAR_GEO_ROWS;      // rows per warp; the CTA tile is 32 x (8 * kGeoRows)
 constexpr int kGeoFrames = NEXAR_GEO_FRAMES;  // frames of one clip per CTA
-enum { GEO_GENERAL = 0, GEO_FILL = 1, GEO_INTERIOR = 2 };
-constexpr unsigned kTailFlags = NEXAR_GRAYSCALE | NEXAR_NOISE | NEXAR_BLUR | NEXAR_POSTERIZE | NEXAR_SOLARIZE | NEXAR_INVERT | NEXAR_CUTOUT;
 #ifndef NEXAR_GEO_MINB
-#define NEXAR_GEO_MINB 5  // measured (cfg2 custom step): 5 CTAs/SM 0.511 ms, 4: 0.513, 6: 0.517 (spills)
+#define NEXAR_GEO_MINB 4
 #endif
 template <typename DstT, bool TAIL>
 __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
@@ -1512,9 +1601,10 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   const unsigned flags = __float_as_uint(q3.z);
   if (!(flags & NEXAR_AUG)) return;
   const int cs = P.cs;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y0 = blockIdx.y * (8 * kGeoRows) + (threadIdx.x >> 5) * kGeoRows;
-  if (x >= cs || y0 >= cs) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx0 = blockIdx.x * 32, ty0 = (blockIdx.y * 8 + warp) * 4;
+  const int x = tx0 + (lane & 15) * 2, ly = lane >> 4;
+  if (ty0 >= cs) return;
   const float4 q2 = __ldg(fi4 + 2);
   const int4 bx = __ldg((const int4*)fi4 + 1);
   const NexarClipParams* cp = A.params + clip;   // only the rare tail effects read it
@@ -1524,119 +1614,173 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   const float g0 = q2.x, g1 = q2.y, g2 = q2.z, g3 = q2.w, g4 = q3.x, g5 = q3.y;
   int cls = GEO_GENERAL;
   if (affine) {
-    // image of the strip centre +- the half extents of the strip under the linear part (a superset for strips
-    // that stick out of the canvas); 0.01 px of slack for rounding differences against the per-pixel evaluation
-    const float xc = (float)(blockIdx.x * 32 + 16) - half, yc = (float)y0 + 0.5f * (float)kGeoRows - half;
+    // image of the tile centre +- the half extents of the tile under the linear part (a superset for tiles that stick
+    // out of the canvas); 0.01 px of slack for rounding differences against the per-pixel evaluation
+    const float xc = (float)(tx0 + 16) - half, yc = (float)(ty0 + 2) - half;
     const float sxc = fmaf(fmaf(yc, g1, xc * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
     const float syc = fmaf(fmaf(yc, g4, xc * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
-    const float hr = 0.5f * (float)(kGeoRows - 1);
-    const float ex = (15.5f * fabsf(g0) + hr * fabsf(g1)) * half + 0.01f;
-    const float ey = (15.5f * fabsf(g3) + hr * fabsf(g4)) * half + 0.01f;
+    const float ex = (15.5f * fabsf(g0) + 1.5f * fabsf(g1)) * half + 0.01f;
+    const float ey = (15.5f * fabsf(g3) + 1.5f * fabsf(g4)) * half + 0.01f;
     const float xmin = sxc - ex, xmax = sxc + ex, ymin = syc - ey, ymax = syc + ey;
+    const float fby0 = (float)B.by0, fby1 = (float)B.by1, fbx0 = (float)B.bx0, fbx1 = (float)B.bx1;
     const bool inside = xmin >= 0.0f && xmax <= fcs - 1.0f && ymin >= 0.0f && ymax <= fcs - 1.0f;
-    const bool above = ymax + 1.0f < (float)B.by0, below = ymin >= (float)B.by1;
-    const bool left = xmax + 1.0f < (float)B.bx0, right = xmin >= (float)B.bx1;
-    const bool interior = xmin >= (float)B.bx0 && xmax <= (float)B.bx1 - 1.0f && ymin >= (float)B.by0 && ymax <= (float)B.by1 - 1.0f;
-    cls = (inside && (above || below || left || right)) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
+    const bool outside_box = ymax + 1.0f < fby0 || ymin >= fby1 || xmax + 1.0f < fbx0 || xmin >= fbx1;
+    const bool interior = xmin >= fbx0 && xmax <= fbx1 - 1.0f && ymin >= fby0 && ymax <= fby1 - 1.0f;
+    cls = (inside && outside_box) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
   }
-  const int fstride = A.bh * A.bw;  // float4 elements per intermediate frame
-  const float4* const fr0 = A.inter + (int64_t)frame0 * fstride - (B.by0 * A.bw + B.bx0);  // frame t0, indexed by canvas (y, x)
-  const float xb = (float)x - half + 0.5f;
-  const float xg0 = xb * g0, xg3 = xb * g3;
+  if (x >= cs) return;
+  const bool has2 = x + 1 < cs;
+  const int bw = A.bw;
+  const int fstride = A.bh * bw;  // pixels per intermediate frame
+  const uint2* const fr0 = A.inter + ((int64_t)frame0 * fstride - (B.by0 * bw + B.bx0));  // frame t0, indexed by canvas (y, x)
   DstT* const obase0 = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t0 * A.st);
-  const int osy = (int)A.sy, osc = (int)A.sc;
-  const int off0 = y0 * osy + x * (int)A.sx;
+  const int osy = (int)A.sy, osc = (int)A.sc, osx = (int)A.sx;
+  const bool vec2 = A.sx == 1 && ((A.sy | A.sc | A.sb | A.st) & 1) == 0 && (((uintptr_t)A.dst) & (2 * sizeof(DstT) - 1)) == 0;
   // TAIL: some clip of the batch has an effect after the affine step (grayscale .. cutout); the common case compiles without them
   const bool tail_fx = TAIL && (flags & kTailFlags) != 0u;
-  const char* const fr0b = (const char*)fr0;
-  const char* const ob0b = (const char*)obase0;
-  const int64_t fbytes = (int64_t)fstride * 16, stbytes = A.st * (int64_t)sizeof(DstT);
+  const float nsr = A.nscale[0], nsg = A.nscale[1], nsb = A.nscale[2], nbr = A.nbias[0], nbg = A.nbias[1], nbb = A.nbias[2];
+  const float xb = (float)x - half + 0.5f;
+  const float xg0[2] = {xb * g0, has2 ? (xb + 1.0f) * g0 : xb * g0}, xg3[2] = {xb * g3, has2 ? (xb + 1.0f) * g3 : xb * g3};
+  const int64_t fbytes = (int64_t)fstride * 8, stbytes = A.st * (int64_t)sizeof(DstT);
+
 #pragma unroll 1
-  for (int k = 0; k < kGeoRows; ++k) {
-    const int y = y0 + k;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int y = ty0 + ly + 2 * pass;
     if (y >= cs) break;
-    // ---- geometry of this pixel, shared by the frames of the clip ----
-    int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-    float w00 = 0.0f, w01 = 0.0f, w10 = 0.0f, w11 = 0.0f, m = 1.0f;
-    if (cls == GEO_FILL) {
-      // pad colour only
-    } else if (affine) {
-      // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
+    // ---- geometry of this lane's two pixels, shared by the frames of the clip ----
+    GeoPx q[2];
+    float t0q[2], pmq[2];
+    if (cls != GEO_FILL) {
       const float yb = (float)y - half + 0.5f;
-      const float gx = fmaf(yb, g1, xg0) + g2;
-      const float gy = fmaf(yb, g4, xg3) + g5;
-      const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
-      const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
-      const float x0f = floorf(ix), y0f = floorf(iy);
-      const float wx1 = ix - x0f, wy1 = iy - y0f;
-      const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-      if (cls == GEO_INTERIOR) {
-        o00 = (int)y0f * A.bw + (int)x0f;
-        o01 = o00 + 1; o10 = o00 + A.bw; o11 = o10 + 1;
-        w00 = wx0 * wy0; w01 = wx1 * wy0; w10 = wx0 * wy1; w11 = wx1 * wy1;
-      } else {
-        // clamp before the int cast so wild matrices cannot overflow
-        const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
-        const int yq = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
-        const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
-        const bool iny0 = (unsigned)yq < (unsigned)cs, iny1 = (unsigned)(yq + 1) < (unsigned)cs;
-        const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
-        m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
-        const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
-        const bool cy0 = yq >= B.by0 && yq < B.by1, cy1 = yq + 1 >= B.by0 && yq + 1 < B.by1;
-        const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
-        const int xc0 = min(max(x0, B.bx0), B.bx1 - 1), xc1 = min(max(x0 + 1, B.bx0), B.bx1 - 1);
-        const int yc0 = min(max(yq, B.by0), B.by1 - 1) * A.bw, yc1 = min(max(yq + 1, B.by0), B.by1 - 1) * A.bw;
-        o00 = yc0 + xc0; o01 = yc0 + xc1; o10 = yc1 + xc0; o11 = yc1 + xc1;
-        w00 = bx0w * by0w; w01 = bx1w * by0w; w10 = bx0w * by1w; w11 = bx1w * by1w;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        GeoPx& g = q[e];
+        const int xe = has2 ? x + e : x;
+        g.m = 1.0f;
+        if (affine) {
+          // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
+          const float gx = fmaf(yb, g1, xg0[e]) + g2;
+          const float gy = fmaf(yb, g4, xg3[e]) + g5;
+          const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
+          const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const float wx1 = ix - x0f, wy1 = iy - y0f;
+          const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+          if (cls == GEO_INTERIOR) {
+            g.o00 = (int)y0f * bw + (int)x0f;
+            g.o01 = g.o00 + 1; g.o10 = g.o00 + bw; g.o11 = g.o10 + 1;
+            g.w00 = wx0 * wy0; g.w01 = wx1 * wy0; g.w10 = wx0 * wy1; g.w11 = wx1 * wy1;
+            g.wc = 1.0f;
+          } else {
+            // clamp before the int cast so wild matrices cannot overflow
+            const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
+            const int yq = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
+            const bool inx0 = (unsigned)x0 < (unsigned)cs, inx1 = (unsigned)(x0 + 1) < (unsigned)cs;
+            const bool iny0 = (unsigned)yq < (unsigned)cs, iny1 = (unsigned)(yq + 1) < (unsigned)cs;
+            const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
+            g.m = (ax0 + ax1) * (ay0 + ay1);                      // interpolated ones-mask
+            const bool cx0 = x0 >= B.bx0 && x0 < B.bx1, cx1 = x0 + 1 >= B.bx0 && x0 + 1 < B.bx1;
+            const bool cy0 = yq >= B.by0 && yq < B.by1, cy1 = yq + 1 >= B.by0 && yq + 1 < B.by1;
+            const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
+            const int xc0 = min(max(x0, B.bx0), B.bx1 - 1), xc1 = min(max(x0 + 1, B.bx0), B.bx1 - 1);
+            const int yc0 = min(max(yq, B.by0), B.by1 - 1) * bw, yc1 = min(max(yq + 1, B.by0), B.by1 - 1) * bw;
+            g.o00 = yc0 + xc0; g.o01 = yc0 + xc1; g.o10 = yc1 + xc0; g.o11 = yc1 + xc1;
+            g.w00 = bx0w * by0w; g.w01 = bx1w * by0w; g.w10 = bx0w * by1w; g.w11 = bx1w * by1w;
+            g.wc = (bx0w + bx1w) * (by0w + by1w);
+          }
+        } else {
+          // no affine: the pixel itself when it is content, the pad colour otherwise
+          const bool in = y >= B.by0 && y < B.by1 && xe >= B.bx0 && xe < B.bx1;
+          g.o00 = g.o01 = g.o10 = g.o11 = min(max(y, B.by0), B.by1 - 1) * bw + min(max(xe, B.bx0), B.bx1 - 1);
+          g.w00 = g.wc = in ? 1.0f : 0.0f;
+          g.w01 = g.w10 = g.w11 = 0.0f;
+        }
+        t0q[e] = -kQ15Inv * g.wc;
+        pmq[e] = g.m - g.wc;
       }
-    } else {
-      // no affine: the pixel itself when it is content, the pad colour otherwise
-      const bool in = y >= B.by0 && y < B.by1 && x >= B.bx0 && x < B.bx1;
-      o00 = o01 = o10 = o11 = min(max(y, B.by0), B.by1 - 1) * A.bw + min(max(x, B.bx0), B.bx1 - 1);
-      w00 = in ? 1.0f : 0.0f;
     }
+    const int off = y * osy + x * osx;
     // ---- the frames (fully unrolled).  The per-frame base pointers are made opaque so that every address below
     // is ONE multiply-add (IMAD.WIDE index * size + base) instead of a 64-bit add chain ----
-    const int off = off0 + k * osy;
 #pragma unroll
     for (int f = 0; f < kGeoFrames; ++f) {
       if (t0 + f >= t1) break;
       const float4 padv = __ldg(fi4 + 5 * f);  // FrameInfo is five float4; the pad colour comes first
-      const float4* fr = (const float4*)(fr0b + f * fbytes);
-      DstT* ob = (DstT*)(ob0b + f * stbytes);
+      const uint2* fr = (const uint2*)((const char*)fr0 + f * fbytes);
+      DstT* ob = (DstT*)((char*)obase0 + f * stbytes);
       asm volatile("" : "+l"(fr));
       asm volatile("" : "+l"(ob));
-      float r = padv.x, g = padv.y, b = padv.z;
+      float rr[2] = {padv.x, padv.x}, gg[2] = {padv.y, padv.y}, bb[2] = {padv.z, padv.z};
       if (cls != GEO_FILL) {
-        const float4 v00 = __ldg(fr + o00), v01 = __ldg(fr + o01), v10 = __ldg(fr + o10), v11 = __ldg(fr + o11);
-        r = m * fmaf(padv.x, m, fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00))));
-        g = m * fmaf(padv.y, m, fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00))));
-        b = m * fmaf(padv.z, m, fmaf(v11.z, w11, fmaf(v10.z, w10, fmaf(v01.z, w01, v00.z * w00))));
+        uint2 v[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          v[e][0] = fr[q[e].o00]; v[e][1] = fr[q[e].o01]; v[e][2] = fr[q[e].o10]; v[e][3] = fr[q[e].o11];
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const GeoPx& g = q[e];
+          const float sr = fmaf(q15_r(v[e][3]), g.w11, fmaf(q15_r(v[e][2]), g.w10, fmaf(q15_r(v[e][1]), g.w01, q15_r(v[e][0]) * g.w00)));
+          const float sg = fmaf(q15_g(v[e][3]), g.w11, fmaf(q15_g(v[e][2]), g.w10, fmaf(q15_g(v[e][1]), g.w01, q15_g(v[e][0]) * g.w00)));
+          const float sb = fmaf(q15_b(v[e][3]), g.w11, fmaf(q15_b(v[e][2]), g.w10, fmaf(q15_b(v[e][1]), g.w01, q15_b(v[e][0]) * g.w00)));
+          if (cls == GEO_INTERIOR) {  // m = wc = 1
+            rr[e] = fmaf(sr, kQ15Inv, -kQ15Inv);
+            gg[e] = fmaf(sg, kQ15Inv, -kQ15Inv);
+            bb[e] = fmaf(sb, kQ15Inv, -kQ15Inv);
+          } else {
+            rr[e] = g.m * fmaf(sr, kQ15Inv, fmaf(padv.x, pmq[e], t0q[e]));
+            gg[e] = g.m * fmaf(sg, kQ15Inv, fmaf(padv.y, pmq[e], t0q[e]));
+            bb[e] = g.m * fmaf(sb, kQ15Inv, fmaf(padv.z, pmq[e], t0q[e]));
+          }
+        }
       }
       if (tail_fx) {
         const int frame = frame0 + f;
         const int idx = y * cs + x;
-        if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
-        if (flags & NEXAR_NOISE) {
-          const unsigned base = (unsigned)((frame * 3) * cs * cs + idx);
-          r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
-          g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
-          b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+        bool to_canvas = false;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (e == 1 && !has2) break;
+          float r = rr[e], g = gg[e], b = bb[e];
+          if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+          if (flags & NEXAR_NOISE) {
+            const unsigned base = (unsigned)((frame * 3) * cs * cs + idx + e);
+            r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+            g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + cs * cs), cp->noise_level, g));
+            b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * cs * cs), cp->noise_level, b));
+          }
+          if (flags & NEXAR_BLUR) {  // the blur kernel finishes the chain from the planar canvas
+            float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
+            cv[idx + e] = r;
+            cv[cs * cs + idx + e] = g;
+            cv[2 * cs * cs + idx + e] = b;
+            to_canvas = true;
+            continue;
+          }
+          point_effects(r, g, b, cp, flags, y, x + e);
+          rr[e] = r; gg[e] = g; bb[e] = b;
         }
-        if (flags & NEXAR_BLUR) {
-          float* cv = A.canvas + (size_t)frame * 3 * cs * cs;
-          cv[idx] = r;
-          cv[cs * cs + idx] = g;
-          cv[2 * cs * cs + idx] = b;
-          continue;
-        }
-        point_effects(r, g, b, cp, flags, y, x);
+        if (to_canvas) continue;
       }
       // nscale / nbias are 1 / 0 when the output is not normalised
-      store_out_global<DstT>(ob + off, fmaf(r, A.nscale[0], A.nbias[0]));
-      store_out_global<DstT>(ob + (off + osc), fmaf(g, A.nscale[1], A.nbias[1]));
-      store_out_global<DstT>(ob + (off + 2 * osc), fmaf(b, A.nscale[2], A.nbias[2]));
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        rr[e] = fmaf(rr[e], nsr, nbr); gg[e] = fmaf(gg[e], nsg, nbg); bb[e] = fmaf(bb[e], nsb, nbb);
+      }
+      if (vec2 && has2) {
+        store_pair<DstT>(ob + off, rr[0], rr[1]);
+        store_pair<DstT>(ob + (off + osc), gg[0], gg[1]);
+        store_pair<DstT>(ob + (off + 2 * osc), bb[0], bb[1]);
+      } else {
+        store_out_global<DstT>(ob + off, rr[0]);
+        store_out_global<DstT>(ob + (off + osc), gg[0]);
+        store_out_global<DstT>(ob + (off + 2 * osc), bb[0]);
+        if (has2) {
+          store_out_global<DstT>(ob + (off + osx), rr[1]);
+          store_out_global<DstT>(ob + (off + osx + osc), gg[1]);
+          store_out_global<DstT>(ob + (off + osx + 2 * osc), bb[1]);
+        }
+      }
     }
   }
 }
@@ -1696,6 +1840,31 @@ static int sm_count() {  // of the current device (cached per device)
   return cached[dev];
 }
 
+// launch of the fast resize kernel; cluster > 0: the `cluster` bands of a frame form one thread-block cluster (fused path)
+template <typename Kern>
+static cudaError_t launch_fast(Kern kern, dim3 grid, int nt, size_t smem, cudaStream_t st, int cluster, const DevPlan& P,
+                               const KArgs& K) {
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(nt);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (cluster > 0) {
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, P, K);
+}
+
 template <typename SrcT, typename DstT>
 static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K, int aug_mode, int blur_mode) {
   cudaStream_t st = (cudaStream_t)a->stream;
@@ -1706,9 +1875,21 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, (size_t)a->n_clips * sizeof(unsigned), st));
   const int vis_rows = imin(p->g.resize_h, p->g.canvas);
   const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
-  int nbands;
   const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
                         a->src_row_stride % 16 == 0 && ((uintptr_t)a->src % 16) == 0;
+  bool tail_done = false;  // K2 / K3's work has already been enqueued
+  int nbands = 1;
+  auto launch_tail = [&]() {  // K1.5 + K2 + K3 (K.pass == 4: only the clips whose maximum was > 1)
+    const int cs = P.cs;
+    frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
+    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
+    const dim3 ggrid((cs + 31) / 32, (cs + 31) / 32, a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
+    if (a->any_flags & kTailFlags)
+      geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
+    else
+      geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
+    g_launches += 3;
+  };
   if (use_fast) {
     const int need_threads = imax(P.src_w * 3 / 16, imin(P.rw, P.cs));
     // Bands per frame: every band re-reads the source rows it shares with its neighbour and pays the CTA prologue, so
@@ -1721,45 +1902,35 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
       nbands = imin(8, ((9 * slots) / 2 + nf - 1) / nf);
     }
     nbands = imax(1, imin(nbands, imin(kMaxBands, vis_rows)));
+    // Variant 4: augmented batches take the fused kernel, the bands of a frame being one cluster (1, 2, 4 or 8 CTAs).
+    // Measured on B200 it is not faster than K1 + K2 + K3 (the SMs are issue-bound either way and K2 / K3 run at twice
+    // the occupancy), so it is not the default; it does have the lowest DRAM traffic (1.12x algorithmic).
+    const bool fused = aug_mode && g_resize_variant == 4;
+    if (fused) {
+      int c = 1;
+      while (2 * c <= nbands && 2 * c <= 8) c *= 2;
+      nbands = c;
+    }
     const int kx = P.kx_al;
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
     K.pass = 0;
-    const bool use_tma = g_resize_variant == 3;
     const int ng = (kx / 2 + 3) / 4;
     const int nt_fast = need_threads <= 256 ? 256 : need_threads <= 320 ? 320 : 384;
-    const size_t smem_fast = smem + (size_t)ng * nt_fast * 16 + (size_t)(P.n_pairs + 1) * 16;  // measured slower than the register-prefetch kernel (0.44 vs 0.39 ms at cfg2)
-    const size_t stage_bytes = 2 * (size_t)P.src_w * 3;
-    const int ns = need_threads <= 256 ? NEXAR_STAGES : (stage_bytes > 8192 ? 4 : NEXAR_STAGES);
-    const size_t smem_tma = smem + ns * stage_bytes + 16 * ns;
+    const size_t smem_fast = smem + (size_t)ng * nt_fast * 16 + (size_t)(P.n_pairs + 1) * 16;
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
 #define NEXAR_FAST_RS(KXV, NTV, MB, RSV)                                                                          \
   {                                                                                                               \
-    auto kern = resize_fast_kernel<KXV, NTV, MB, RSV, DstT>;                                                       \
-    if (smem_fast > 48 * 1024)                                                                                    \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));           \
-    kern<<<grid, NTV, smem_fast, st>>>(P, K);                                                                      \
+    if (fused)                                                                                                    \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, true>, grid, NTV, smem_fast, st, nbands, P, K)); \
+    else                                                                                                          \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, false>, grid, NTV, smem_fast, st, 0, P, K)); \
   }
 #define NEXAR_FAST(KXV, NTV, MB) NEXAR_FAST_RS(KXV, NTV, MB, 0)
 // tightly packed 720p / 1080p rows get the row stride as a compile-time constant (immediate load offsets)
 #define NEXAR_FAST_SPEC(KXV, NTV, MB, RSV) \
   if (a->src_row_stride == RSV) NEXAR_FAST_RS(KXV, NTV, MB, RSV) else NEXAR_FAST_RS(KXV, NTV, MB, 0)
-#define NEXAR_TMA(KXV, NTV, MB, NSV)                                                                              \
-  {                                                                                                               \
-    auto kern = resize_tma_kernel<KXV, NTV, MB, NSV, DstT>;                                                        \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));              \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
-    kern<<<grid, NTV, smem_tma, st>>>(P, K);                                                                       \
-  }
-    if (use_tma) {
-      if (need_threads <= 256) {
-        if (kx == 10) NEXAR_TMA(10, 256, NEXAR_MINB, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 256, NEXAR_MINB, NEXAR_STAGES) else NEXAR_TMA(20, 256, 2, NEXAR_STAGES)
-      } else if (ns == 4) {
-        if (kx == 10) NEXAR_TMA(10, 384, 2, 4) else if (kx == 14) NEXAR_TMA(14, 384, 2, 4) else NEXAR_TMA(20, 384, 2, 4)
-      } else {
-        if (kx == 10) NEXAR_TMA(10, 384, 2, NEXAR_STAGES) else if (kx == 14) NEXAR_TMA(14, 384, 2, NEXAR_STAGES) else NEXAR_TMA(20, 384, 2, NEXAR_STAGES)
-      }
-    } else if (need_threads <= 256) {
+    if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST_SPEC(14, 256, NEXAR_MINB, 3840) else NEXAR_FAST(20, 256, 2)
     } else if (need_threads <= 320) {
       if (kx == 10) NEXAR_FAST_SPEC(10, 320, 2, 3840) else if (kx == 14) NEXAR_FAST(14, 320, 2) else NEXAR_FAST(20, 320, 2)
@@ -1769,16 +1940,21 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
 #undef NEXAR_FAST_SPEC
 #undef NEXAR_FAST
 #undef NEXAR_FAST_RS
-#undef NEXAR_TMA
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n++ + 1], st);
     // fix-up of clips whose maximum was <= 1 (not divided by 255): their values live in [0,1], below the
-    // resolution of the 15-bit staging, so the rare second pass uses the fp32 kernel.  Same band count:
-    // the gray partial sums are indexed by band.
+    // resolution of the 15-bit staging, so the rare second pass uses the fp32 resample.
+    // K1.5 / K2 / K3 for the clips whose maximum was > 1 (pass 4: the others are skipped, see fixup_frame_kernel)
+    if (aug_mode && !fused) {
+      K.pass = 4;
+      launch_tail();
+    }
+    // one launch that finishes the clips whose maximum was <= 1 completely (a no-op CTA per frame otherwise)
     K.pass = 1;
     const size_t gsm = (size_t)P.src_w * 3 * sizeof(float);
     if (gsm > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(resize_general_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-    resize_general_kernel<SrcT, DstT><<<grid, 256, gsm, st>>>(P, K);
+      CUDA_TRY(cudaFuncSetAttribute(fixup_frame_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    fixup_frame_kernel<SrcT, DstT><<<nf, 256, gsm, st>>>(P, K);
+    tail_done = true;
     g_launches += 2;
   } else {
     nbands = imax(1, imin(kMaxBands, vis_rows / 24));
@@ -1802,20 +1978,14 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
       g_launches += 2;
     }
   }
-  if (aug_mode) {
+  if (aug_mode && !tail_done) {
+    K.pass = 0;
+    launch_tail();
+  }
+  if (aug_mode && blur_mode) {
     const int cs = P.cs;
-    frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
-    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
-    const dim3 ggrid((cs + 31) / 32, (cs + 8 * kGeoRows - 1) / (8 * kGeoRows), a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
-    if (a->any_flags & kTailFlags)
-      geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
-    else
-      geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
-    g_launches += 3;
-    if (blur_mode) {
-      blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
-      ++g_launches;
-    }
+    blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
+    ++g_launches;
   }
   CUDA_TRY(cudaGetLastError());
   return NEXAR_OK;
@@ -1837,7 +2007,6 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   const size_t esz = p->src_dtype == NEXAR_SRC_U8 ? 1 : 4;
   if (a->src_row_stride < (int64_t)(p->g.src_w * 3 * esz)) return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
 
-  if ((int64_t)a->n_clips * a->frames_per_clip > 65535) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: more than 65535 frames per call");
   Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace, a->any_flags);
   KArgs K;
   K.src = a->src;
