@@ -10,5 +10,7 @@ Parity pinning: the reference ships no tests or golden vectors for this path
 (SURVEY.md section 4), so the oracle is pinned against outputs of the unmodified
 reference itself, imported in the build container by ``oracle/ref_import.py``
 and frozen by ``tests/golden/make_golden.py`` into ``tests/golden/*.npz``
-(torch 2.11.0 / torchvision 0.26.0).
+(torch 2.11.0 / torchvision 0.26.0).  The sampler / sensor restatements are pinned the
+same way against the unmodified reference Datasets (``tests/golden/make_dataset_golden.py``
+-> ``dataset_golden.json``, ``dataset_sensor.npz``).
 """

@@ -1,9 +1,12 @@
 """Integer restatement of the reference's temporal window selection (R1).
 TEST INFRASTRUCTURE ONLY.
 
-The reference Datasets cannot be imported here (decord / matplotlib missing,
-SURVEY.md section 8c), so this follows them line by line over a fake frame
-count.  Integer-only, hence exact.
+Follows the reference Datasets line by line over a frame count.  Integer-only, hence
+exact.  Parity pinning: tests/test_dataset_golden.py holds it to what the UNMODIFIED
+``NvidiaDashcamDataset`` / ``VideoDataset`` did on a 36-video grid (972 cases, indices and
+``random`` consumption), frozen by tests/golden/make_dataset_golden.py, which imports the
+reference modules with stubs for their missing plotting / decode imports and fake
+``decord.VideoReader`` / ``cv2.VideoCapture`` objects.
 """
 import random as _random
 from typing import List, Optional

@@ -8,10 +8,9 @@ code that stage calls: torchvision 0.26.0 ``transforms/_functional_tensor.py`` /
 libraries are not vendored by the reference and are unpinned there; the
 versions above are the ones the golden vectors were produced with.
 
-Parity pinning: checked against the unmodified reference in
-``tests/test_oracle_vs_golden.py`` (committed fixtures from
-``tests/golden/make_golden.py``) and, where ``/root/reference`` exists, live in
-``tests/test_oracle_vs_reference.py``.
+Parity pinning: checked against outputs of the unmodified reference in
+``tests/test_oracle_vs_golden.py`` (committed fixtures; ``tests/golden/make_golden.py``
+regenerates them where ``/root/reference`` exists).
 
 Frames are handled as float32 ``[C, H, W]`` planes like the reference does.
 """

@@ -1,5 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (never imported by the product): the reference's sensor synchronisation restated with
-the same pandas calls, line for line (nexar_videos.py:318-341), minus the file / cv2 access."""
+the same pandas calls, line for line (nexar_videos.py:318-341), minus the file / cv2 access.  Parity pinning: the product
+path it checks is ALSO held to the sensor rows the unmodified ``_load_and_sync_sensor_data`` returned for 756 cases
+(tests/golden/dataset_sensor.npz, tests/test_dataset_golden.py)."""
 import numpy as np
 import pandas as pd
 

@@ -29,6 +29,7 @@ import pandas as pd
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 REF = os.environ.get("NEXAR_REFERENCE_DIR", "/root/reference")
 
 REGISTRY = {}          # path -> dict(n=frames, fps=float, h=int, w=int)
@@ -134,43 +135,10 @@ def main():
     cases = []
     sensor_arrays = {}
 
-    def add_video(vid, n, fps, fname=None, sensor=None, base=tmp, h=4, w=6):
-        d = os.path.join(base, vid)
-        os.makedirs(d, exist_ok=True)
-        path = os.path.join(d, fname or f"{vid}.mp4")
-        open(path, "wb").close()
-        REGISTRY[path] = dict(n=n, fps=fps, h=h, w=w)
-        if sensor is not None:
-            os.makedirs(os.path.join(d, "signals"), exist_ok=True)
-            sensor.to_csv(os.path.join(d, "signals", "Dashcam-Accelerometer_Acceleration.csv"))
-        return path
-
-    def sensor_table(kind, n_rows, seed, t0=1000.0, rate=50.0):
-        rs = np.random.RandomState(seed)
-        t = t0 + np.arange(n_rows) / rate + (rs.uniform(-0.004, 0.004, n_rows) if kind != "regular" else 0.0)
-        a = rs.normal(0, 1, (n_rows, 4))
-        if kind == "nan":
-            a[rs.uniform(size=a.shape) < 0.15] = np.nan
-        if kind == "short":
-            t = t[: max(2, n_rows // 4)]
-            a = a[: len(t)]
-        return pd.DataFrame({"time_sec": t, "accel_x_G": a[:, 0], "accel_y_G": a[:, 1], "accel_z_G": a[:, 2],
-                             "accel_total_G": a[:, 3]})
-
-    # ---- NvidiaDashcamDataset -------------------------------------------------------------------------------------
-    grid = []
-    vid_no = 0
-    for n in (1, 7, 49, 50, 51, 99, 100, 101, 150, 299, 900, 1200):
-        for fps in (10.0, 29.97, 30.0):
-            vid_no += 1
-            vid = f"v{vid_no:03d}"
-            kind = ("regular", "jitter", "nan", "short", None)[vid_no % 5]
-            sensor = sensor_table(kind, int(n / fps * 50) + 60, vid_no) if kind else None
-            fname = (f"{vid}.mp4", f"anonymized_{vid}.mp4", f"{vid}.mov")[vid_no % 3]
-            add_video(vid, n, fps, fname=fname, sensor=sensor)
-            grid.append(dict(id=vid, video_type=("Normal", "Near Collision", "Collision")[vid_no % 3], n=n, vfps=fps,
-                             sensor_kind=kind, fname=fname,
-                             event_time=[0.0, 0.4, n / fps / 2, n / fps, n / fps + 3.0, float("nan")][vid_no % 6]))
+    from dataset_fixture import build_tree, video_grid
+    grid = video_grid()
+    for path, g in build_tree(tmp, grid).items():
+        REGISTRY[path] = dict(n=g["n"], fps=g["vfps"], h=4, w=6)
     meta = pd.DataFrame([{k: g[k] for k in ("id", "video_type", "event_time")} for g in grid])
     for strategy, time_column, fps_d in (("random", None, (10, 5)), ("center", None, (10, 5)), ("metadata_time", "event_time", (10, 5)),
                                          ("uniform", None, (10, 5)), ("random", None, (8, 2)), ("center", None, (16, 1)),

@@ -168,8 +168,15 @@ def test_deferred_dataset_and_collate_without_cuda():
     assert bad["frames_u8"] is None                                      # any failure is swallowed
     assert isinstance(a["params"]["flip"], bool)
     batch = V.deferred_collate([a, b, bad])
-    assert tuple(batch["frames_u8"].shape) == (2, 50, 48, 64, 3) and batch["valid"] == [True, True, False]
-    assert batch["target"] == ["Normal", "Collision", "Normal"] and len(batch["params"]) == 2
+    assert len(batch["groups"]) == 1 and batch["valid"] == [True, True, False]
+    g = batch["groups"][0]
+    assert tuple(g["frames_u8"].shape) == (2, 50, 48, 64, 3) and g["index"] == [0, 1] and len(g["params"]) == 2
+    assert batch["target"] == ["Normal", "Collision", "Normal"]
+    # a batch that mixes source resolutions is stacked per resolution (the reference transforms before it collates)
+    other = dict(a, frames_u8=torch.zeros(50, 36, 64, 3, dtype=torch.uint8))
+    mixed = V.deferred_collate([a, other, b, bad])
+    assert [tuple(g["frames_u8"].shape[2:4]) for g in mixed["groups"]] == [(48, 64), (36, 64)]
+    assert [g["index"] for g in mixed["groups"]] == [[0, 2], [1]] and mixed["valid"] == [True, True, True, False]
     assert list(V.shard_clips(10, 1, 4)) == [3, 4, 5] and list(V.shard_clips(10, 3, 4)) == [9]
 
 

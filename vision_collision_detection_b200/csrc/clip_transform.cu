@@ -421,6 +421,7 @@ static_assert(sizeof(FrameInfo) == 80, "FrameInfo is five 16-byte words");
 
 struct Workspace {
   unsigned* clip_max;   // [n_clips] non-zero iff some source value of the clip is > 1 (nexar_video_aug.py:814)
+  unsigned* frame_done; // [n_frames] bands of the frame that have finished K1 (the last one publishes the FrameInfo); follows clip_max
   unsigned long long* gray_partial;  // [2][n_frames][kMaxBands] fixed-point (2^-22) gray sums: exact, order-independent
   FrameInfo* finfo;     // [n_frames] per-frame constants for K2/K3, written by K1.5
   uint2* inter;         // [n_frames][bh][bw]   q15 RGBX pixels (8 bytes), brightness-adjusted, then colour-adjusted in place
@@ -435,7 +436,8 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base, unsig
   size_t off = 0;
   char* b = (char*)base;
   w.clip_max = (unsigned*)(b + off);
-  off = align_up(off + (size_t)n_clips * sizeof(unsigned), 256);
+  w.frame_done = w.clip_max + n_clips;  // one memset clears both
+  off = align_up(off + ((size_t)n_clips + nf) * sizeof(unsigned), 256);
   w.gray_partial = (unsigned long long*)(b + off);
   off = align_up(off + 2 * nf * kMaxBands * sizeof(unsigned long long), 256);
   w.finfo = (FrameInfo*)(b + off);
@@ -471,6 +473,8 @@ struct KArgs {
   int normalize;
   float nscale[3], nbias[3];  // out = v * nscale + nbias  ((v - mean) / std)
   unsigned* clip_max;
+  unsigned* frame_done;
+  int finfo_by_k1;  // the fast resize kernel publishes the FrameInfo of every frame itself (K1.5 folded into K1)
   unsigned long long* gray_partial;
   FrameInfo* finfo;
   uint2* inter;
@@ -845,6 +849,7 @@ template <typename DstT, int NT, bool CLUSTER>
 __device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KArgs& A, const NexarClipParams* cp,
                                                       unsigned flags, int frame, int clip, int t, int band, int nb,
                                                       const Box& B, int i0, int i1, int slot);
+__device__ __forceinline__ void write_frame_info(const DevPlan& P, const KArgs& A, int frame, int slot, int nbands);
 
 // FUSED: the nb bands of a frame form one thread-block cluster; after the resize the cluster goes on, in the same
 // launch, with the colour chain (in place on the band's own rows) and the affine gather + store (see
@@ -1108,6 +1113,16 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   if constexpr (FUSED) {
     // aug is a property of the clip, hence uniform over the cluster: either every CTA of it takes the barriers or none
     if (aug) fused_colour_geometry<DstT, NT, true>(P, A, cp, flags, frame, clip, t, band, nb, B, i0, i1, 0);
+  } else {
+    // K1.5 folded in: the last band of the frame to get here publishes the frame's constants for K2 / K3 (gray mean of
+    // the "divided by 255" pass; clips whose maximum turns out to be <= 1 are redone by fixup_frame_kernel anyway)
+    if (A.finfo_by_k1 && tid == 0) {
+      __threadfence();
+      if (atomicAdd(&A.frame_done[frame], 1u) == (unsigned)nb - 1u) {
+        __threadfence();
+        write_frame_info(P, A, frame, 0, nb);
+      }
+    }
   }
 }
 
@@ -1154,23 +1169,19 @@ __device__ __forceinline__ float frame_mean(const KArgs& A, const DevPlan& P, in
   return (float)((double)s / ((double)kGrayFix * (double)(P.cs * P.cs)));
 }
 
-// K1.5: one thread per frame.  Reduces the band partial sums to the frame's gray mean (fixed order:
-// deterministic) and evaluates the colour a zero pad pixel takes after the colour chain.
-// stats[frame] = (pad r, pad g, pad b, contrast_q * mean).
-__global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, int nbands) {
-  const int frame = blockIdx.x * blockDim.x + threadIdx.x;
-  if (frame >= A.n_frames) return;
+// K1.5: the per-frame constants of K2 / K3.  Reduces the band partial sums to the frame's gray mean (fixed order:
+// deterministic) and evaluates the colour a zero pad pixel takes after the colour chain.  One thread per frame: either
+// the last band of the frame to finish the fast resize kernel, or frame_stats_kernel after the general one.
+__device__ __forceinline__ void write_frame_info(const DevPlan& P, const KArgs& A, int frame, int slot, int nbands) {
   const int clip = frame / A.T;
   const NexarClipParams* cp = A.params + clip;
   FrameInfo fi;
   fi.flags = cp->flags;
   fi.reserved = 0;
-  // A.pass == 4: fixup_frame_kernel finishes the clips whose maximum was <= 1 on its own; K2 / K3 skip them
-  if (!(fi.flags & NEXAR_AUG) || (A.pass == 4 && A.clip_max[clip] == 0u)) {
+  if (!(fi.flags & NEXAR_AUG)) {
     A.finfo[frame].flags = 0u;
     return;
   }
-  const int slot = A.clip_max[clip] != 0u ? 0 : 1;
   ColourParams c;
   c.cmean = __fmul_rn(cp->contrast_q, frame_mean(A, P, frame, slot, nbands));
   c.contrast = cp->contrast;
@@ -1187,6 +1198,11 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant_
   fi.contrast = c.contrast; fi.saturation = c.saturation; fi.saturation_q = c.saturation_q; fi.hue = c.hue6;
   A.finfo[frame] = fi;
 }
+__global__ void __launch_bounds__(128) frame_stats_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A, int nbands) {
+  const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= A.n_frames) return;
+  write_frame_info(P, A, frame, A.clip_max[frame / A.T] != 0u ? 0 : 1, nbands);
+}
 
 // K2: contrast/saturation/hue in place on the frame's content box (which always fills the
 // [bh][bw] allocation: letterbox shows every resized row, a crop shows exactly cs x cs of them), 8-byte q15 pixels.
@@ -1201,6 +1217,7 @@ __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __gri
   const float4* fi4 = (const float4*)(A.finfo + frame);
   const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, 6 * hue, -
   if (!(__float_as_uint(q3.z) & NEXAR_AUG)) return;
+  if (A.pass == 4 && A.clip_max[frame / A.T] == 0u) return;  // fixup_frame_kernel finishes those clips on its own
   ColourParams c;
   c.cmean = st.w;
   c.contrast = q3.w;
@@ -1590,6 +1607,13 @@ constexpr int kGeoFrames = NEXAR_GEO_FRAMES;  // frames of one clip per CTA
 #ifndef NEXAR_GEO_MINB
 #define NEXAR_GEO_MINB 4
 #endif
+#ifndef NEXAR_GEO_PASSES
+#define NEXAR_GEO_PASSES 2   // row passes per warp: the warp tile is 32 x (2 * passes) pixels
+#endif
+#ifndef NEXAR_GEO_OPAQUE
+#define NEXAR_GEO_OPAQUE 1   // per-frame base pointers made opaque to the compiler (cheaper addresses, loads stay per frame)
+#endif
+constexpr int kGeoPasses = NEXAR_GEO_PASSES;
 template <typename DstT, bool TAIL>
 __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   const int nchunk = (A.T + kGeoFrames - 1) / kGeoFrames;
@@ -1600,9 +1624,10 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   const float4 q3 = __ldg(fi4 + 3);
   const unsigned flags = __float_as_uint(q3.z);
   if (!(flags & NEXAR_AUG)) return;
+  if (A.pass == 4 && A.clip_max[clip] == 0u) return;  // fixup_frame_kernel finishes those clips on its own
   const int cs = P.cs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tx0 = blockIdx.x * 32, ty0 = (blockIdx.y * 8 + warp) * 4;
+  const int tx0 = blockIdx.x * 32, ty0 = (blockIdx.y * 8 + warp) * (2 * kGeoPasses);
   const int x = tx0 + (lane & 15) * 2, ly = lane >> 4;
   if (ty0 >= cs) return;
   const float4 q2 = __ldg(fi4 + 2);
@@ -1616,11 +1641,12 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   if (affine) {
     // image of the tile centre +- the half extents of the tile under the linear part (a superset for tiles that stick
     // out of the canvas); 0.01 px of slack for rounding differences against the per-pixel evaluation
-    const float xc = (float)(tx0 + 16) - half, yc = (float)(ty0 + 2) - half;
+    constexpr float hr = (float)kGeoPasses - 0.5f;  // half the tile's row extent, centre to centre
+    const float xc = (float)(tx0 + 16) - half, yc = (float)(ty0 + kGeoPasses) - half;
     const float sxc = fmaf(fmaf(yc, g1, xc * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
     const float syc = fmaf(fmaf(yc, g4, xc * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
-    const float ex = (15.5f * fabsf(g0) + 1.5f * fabsf(g1)) * half + 0.01f;
-    const float ey = (15.5f * fabsf(g3) + 1.5f * fabsf(g4)) * half + 0.01f;
+    const float ex = (15.5f * fabsf(g0) + hr * fabsf(g1)) * half + 0.01f;
+    const float ey = (15.5f * fabsf(g3) + hr * fabsf(g4)) * half + 0.01f;
     const float xmin = sxc - ex, xmax = sxc + ex, ymin = syc - ey, ymax = syc + ey;
     const float fby0 = (float)B.by0, fby1 = (float)B.by1, fbx0 = (float)B.bx0, fbx1 = (float)B.bx1;
     const bool inside = xmin >= 0.0f && xmax <= fcs - 1.0f && ymin >= 0.0f && ymax <= fcs - 1.0f;
@@ -1644,7 +1670,7 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   const int64_t fbytes = (int64_t)fstride * 8, stbytes = A.st * (int64_t)sizeof(DstT);
 
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < kGeoPasses; ++pass) {
     const int y = ty0 + ly + 2 * pass;
     if (y >= cs) break;
     // ---- geometry of this lane's two pixels, shared by the frames of the clip ----
@@ -1708,8 +1734,10 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
       const float4 padv = __ldg(fi4 + 5 * f);  // FrameInfo is five float4; the pad colour comes first
       const uint2* fr = (const uint2*)((const char*)fr0 + f * fbytes);
       DstT* ob = (DstT*)((char*)obase0 + f * stbytes);
-      asm volatile("" : "+l"(fr));
-      asm volatile("" : "+l"(ob));
+      if (NEXAR_GEO_OPAQUE) {
+        asm volatile("" : "+l"(fr));
+        asm volatile("" : "+l"(ob));
+      }
       float rr[2] = {padv.x, padv.x}, gg[2] = {padv.y, padv.y}, bb[2] = {padv.z, padv.z};
       if (cls != GEO_FILL) {
         uint2 v[2][4];
@@ -1872,7 +1900,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   const DevPlan& P = p->d;
   const bool covers_source = (p->g.off_y >= 0 && p->g.off_x >= 0 && p->g.off_y + p->g.resize_h <= p->g.canvas &&
                               p->g.off_x + p->g.resize_w <= p->g.canvas);
-  CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, (size_t)a->n_clips * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, ((size_t)a->n_clips + nf) * sizeof(unsigned), st));
   const int vis_rows = imin(p->g.resize_h, p->g.canvas);
   const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
   const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
@@ -1881,14 +1909,17 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   int nbands = 1;
   auto launch_tail = [&]() {  // K1.5 + K2 + K3 (K.pass == 4: only the clips whose maximum was > 1)
     const int cs = P.cs;
-    frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
+    if (!K.finfo_by_k1) {
+      frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
+      ++g_launches;
+    }
     colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
-    const dim3 ggrid((cs + 31) / 32, (cs + 31) / 32, a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
+    const dim3 ggrid((cs + 31) / 32, (cs + 16 * kGeoPasses - 1) / (16 * kGeoPasses), a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
     if (a->any_flags & kTailFlags)
       geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
     else
       geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
-    g_launches += 3;
+    g_launches += 2;
   };
   if (use_fast) {
     const int need_threads = imax(P.src_w * 3 / 16, imin(P.rw, P.cs));
@@ -1915,6 +1946,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const size_t smem = 2 * (size_t)((P.src_w * 3 + kx * 3 + 15) & ~7) * sizeof(unsigned short);
     dim3 grid(nbands, nf);
     K.pass = 0;
+    K.finfo_by_k1 = aug_mode && !fused;
     const int ng = (kx / 2 + 3) / 4;
     const int nt_fast = need_threads <= 256 ? 256 : need_threads <= 320 ? 320 : 384;
     const size_t smem_fast = smem + (size_t)ng * nt_fast * 16 + (size_t)(P.n_pairs + 1) * 16;
@@ -2027,6 +2059,8 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
     K.nbias[c] = a->normalize ? (float)(-(double)a->mean[c] * inv) : 0.0f;
   }
   K.clip_max = w.clip_max;
+  K.frame_done = w.frame_done;
+  K.finfo_by_k1 = 0;
   K.gray_partial = w.gray_partial;
   K.finfo = w.finfo;
   K.inter = w.inter;

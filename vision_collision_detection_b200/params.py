@@ -117,6 +117,15 @@ def inverse_affine_matrix(angle: float, translate: Sequence[float], scale: float
     return m
 
 
+def draw_noise_seed() -> Tuple[int, int]:
+    """Two 32-bit words from torch's GLOBAL generator - the stream the reference's ``torch.randn_like`` consumes
+    (nexar_video_aug.py:245) - so ``torch.manual_seed`` controls the noise here as it does there, and Python's
+    ``random`` draw order is untouched."""
+    import torch
+    a, b = torch.randint(0, 2 ** 32, (2,), dtype=torch.int64).tolist()
+    return int(a), int(b)
+
+
 def gaussian_taps(sigma: float) -> np.ndarray:
     """nexar_video_aug.py:253 kernel size + tv _get_gaussian_kernel1d, float32."""
     ksize = int(sigma * 4) * 2 + 1
@@ -174,7 +183,10 @@ def pack_clip_params(records: Sequence[Dict[str, Any]], canvas: int,
             if p["apply_noise"]:
                 flags |= _lib.NOISE
                 fview[i, _F["noise_level"]] = aug_cfg.noise_level
-                words[i, _F["noise_seed"]:_F["noise_seed"] + 2] = rec.get("noise_seed", (0x1234567, 0x89ABCDE))
+                # per-clip seed of the counter-based generator: the record's (drawn by sample_params, so a record
+                # reproduces its noise), else a fresh draw - never a constant (the reference draws fresh
+                # torch.randn_like noise for every frame of every call, nexar_video_aug.py:245)
+                words[i, _F["noise_seed"]:_F["noise_seed"] + 2] = rec.get("noise_seed") or draw_noise_seed()
             if p["apply_blur"]:
                 taps = gaussian_taps(aug_cfg.blur_sigma)
                 if len(taps) > _lib.MAX_BLUR_TAPS:

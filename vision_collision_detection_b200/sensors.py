@@ -30,6 +30,14 @@ def find_sensor_path(video_path: Optional[str], sensor_subdir: str = "signals") 
 def read_sensor_csv(path: str):
     """-> (time_sec [N] float64, accel [N,4] float64).  Same columns ``pd.read_csv(path, index_col=0)`` would
     expose by name; empty cells become NaN as in pandas."""
+    try:   # the reference's own call (nexar_videos.py:313): pandas' default float parser is NOT round-trip exact (it can be
+        # one ulp off Python's float()), so bit-equality with the reference needs the same parser
+        import pandas as pd
+        df = pd.read_csv(path, index_col=0)
+        return (df["time_sec"].to_numpy(dtype=np.float64),
+                df[list(SENSOR_COLUMNS)].to_numpy(dtype=np.float64))
+    except ImportError:
+        pass
     with open(path, newline="") as f:
         rows = list(csv.reader(f))
     if len(rows) < 2:

@@ -32,7 +32,7 @@ import torch.nn as nn
 
 from . import _lib
 from .engine import _SRC, _alloc_out, get_engine
-from .params import VideoAugmentation, pack_clip_params
+from .params import VideoAugmentation, draw_noise_seed, pack_clip_params
 
 
 class _Stage:
@@ -107,6 +107,8 @@ class GpuVideoTransform(nn.Module):
                 rec["flip"] = rng.random() < self.horizontal_flip_prob      # :748
             if self.video_aug is not None:
                 rec["aug"] = self.video_aug._sample_augmentation_parameters((3, 0, cs, cs), rng)  # :290
+                if rec["aug"].get("apply_noise"):      # fresh noise per clip and call (torch's generator, as :245)
+                    rec["noise_seed"] = draw_noise_seed()
             recs.append(rec)
         return recs
 
@@ -162,6 +164,14 @@ class GpuVideoTransform(nn.Module):
             if frame_index.dim() != 2:
                 raise ValueError("frame_index must be [n_clips, frames_per_clip]")
             n_clips, t_out = frame_index.shape
+            if frame_index.numel() == 0:
+                raise ValueError("frame_index is empty")
+            # the kernels turn these into raw byte offsets: refuse anything outside the frame pool (a host tensor is
+            # checked here; a device tensor is checked on the device without a sync, the failure surfaces at the next one)
+            if frame_index.is_cuda:
+                torch._assert_async(((frame_index >= 0) & (frame_index < b * t)).all())
+            elif int(frame_index.min()) < 0 or int(frame_index.max()) >= b * t:
+                raise ValueError(f"frame_index must lie in [0, {b * t}); got [{int(frame_index.min())}, {int(frame_index.max())}]")
             offsets = (frame_index.to(device=frames.device, dtype=torch.int64) * frame_bytes).reshape(-1).contiguous()
         else:
             n_clips, t_out = b, t

@@ -84,6 +84,28 @@ def model_frame_subsample(num_frames: int) -> List[int]:
 # ---------------------------------------------------------------------------------
 # Dataset mirror
 # ---------------------------------------------------------------------------------
+def find_video_path(video_id, base_dirs: Sequence[str]) -> Optional[str]:
+    """``_find_video_and_sensor_paths`` (nexar_videos.py:17-36): the FIRST entry of ``os.listdir(<base>/<id>)`` that ends
+    in ``.mp4`` or ``.mov`` (e.g. the ``anonymized_<id>.mp4`` files of some source directories), in the first base
+    directory that has one; None when there is none."""
+    import os
+    for base in base_dirs:
+        if base is None:
+            continue
+        video_dir = os.path.join(base, str(video_id))
+        if not os.path.exists(video_dir):
+            continue
+        for name in os.listdir(video_dir):
+            if name.endswith(".mp4") or name.endswith(".mov"):
+                return os.path.join(video_dir, name)
+    return None
+
+
+def _in_dataloader_worker() -> bool:
+    import torch.utils.data as tud
+    return tud.get_worker_info() is not None
+
+
 def _decord_reader(path: str):
     import decord  # not installed in every image; only needed when no decoder is injected
     return decord.VideoReader(path, ctx=decord.cpu(0))
@@ -130,12 +152,8 @@ class GpuDashcamDataset(Dataset):
             if path is None and path_resolver is not None:
                 path = path_resolver(row["id"])
             if path is None and self.base_dirs[0] is not None:
-                for base in self.base_dirs:
-                    cand = os.path.join(base, str(row["id"]), f"{row['id']}.mp4")
-                    if os.path.exists(cand):
-                        path = cand
-                        break
-                if path is None and not skip_missing:
+                path = find_video_path(row["id"], self.base_dirs)
+                if path is None and not skip_missing:      # nexar_videos.py:80-85: kept, decodes to the zero clip
                     path = os.path.join(self.base_dirs[0], str(row["id"]), f"{row['id']}.mp4")
             if path is None and skip_missing:
                 continue
@@ -154,7 +172,8 @@ class GpuDashcamDataset(Dataset):
         return float(get()) if get is not None else 30.0
 
     def _window(self, reader, row, idx):
-        """-> (frame indices, start, end) of nexar_videos.py:364-435."""
+        """-> (frame indices asked of the decoder, start, end) of nexar_videos.py:364-419; a short window is padded
+        afterwards by repeating the last decoded frame (:428-433)."""
         n = len(reader)
         need = self.fps * self.duration
         ts, vfps = None, 0.0
@@ -162,7 +181,8 @@ class GpuDashcamDataset(Dataset):
             ts = row.get(self.time_column)
             vfps = self._video_fps(reader, idx)
         start = select_start_frame(n, need, self.sample_strategy, random, ts, vfps)
-        return window_indices(n, need, start), start, min(start + need, n)
+        end = min(start + need, n)
+        return list(range(start, end)), start, end      # nexar_videos.py:416-419: the decoder is asked for these only
 
     def _sensor(self, reader, idx, start, end) -> torch.Tensor:
         """nexar_videos.py:453-477 (frame count / fps come from the decoder instead of a second cv2 open)."""
@@ -176,6 +196,14 @@ class GpuDashcamDataset(Dataset):
         row = self.rows[idx]
         need = self.fps * self.duration
         target, vid = row.get("video_type"), row.get("id")
+        if not self.defer and self.transform is not None and _in_dataloader_worker():
+            raise RuntimeError("GpuDashcamDataset(defer=False) runs the CUDA transform inside __getitem__, which cannot "
+                               "work in a DataLoader worker process; use defer=True with deferred_collate + GpuAugLoader "
+                               "(INTEGRATION.md) or num_workers=0")
+        # nexar_videos.py:479-489 swallows EVERY failure and returns an all-zeros clip.  That contract is kept for what
+        # can legitimately fail per item - opening / decoding the video, the window arithmetic (e.g. a NaN timestamp),
+        # the sensor file - but NOT for the GPU transform: a CUDA, library or out-of-memory error there is a bug or a
+        # broken set-up, and training silently on black clips would hide it.
         try:
             reader = self.decoder(self.video_paths[idx])
             indices, start, end = self._window(reader, row, idx)
@@ -184,24 +212,21 @@ class GpuDashcamDataset(Dataset):
                 last = frames[-1] if len(frames) else np.zeros(frames.shape[1:] or (720, 1280, 3), np.uint8)
                 frames = np.concatenate([frames, np.repeat(last[None], need - len(frames), axis=0)], axis=0)
             frames = torch.from_numpy(np.ascontiguousarray(frames[:need]))
-            if self.defer:
-                t = self.transform
-                params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
-                return {"frames_u8": frames, "params": params, "sensor": self._sensor(reader, idx, start, end),
-                        "target": target, "id": vid, "need": need}
-            video = frames.permute(3, 0, 1, 2)                  # nexar_videos.py:441
-            video = self.transform(video) if self.transform else video.float() / 255.0
-            frames = video.permute(1, 2, 3, 0)                  # nexar_videos.py:451
             sensor = self._sensor(reader, idx, start, end)
-            return {"frames": frames, "sensor": sensor, "target": target, "id": vid}
         except Exception:
-            # nexar_videos.py:479-489: swallow everything, return an all-zeros clip of the standard size
             size = (224, 224) if self.transform else (720, 1280)
             if self.defer:
                 return {"frames_u8": None, "params": None, "sensor": torch.zeros(need, 4), "target": target, "id": vid,
                         "need": need}
-            frames = torch.zeros(need, size[0], size[1], 3)
-        return {"frames": frames, "sensor": torch.zeros(need, 4), "target": target, "id": vid}
+            return {"frames": torch.zeros(need, size[0], size[1], 3), "sensor": torch.zeros(need, 4), "target": target,
+                    "id": vid}
+        if self.defer:
+            t = self.transform
+            params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
+            return {"frames_u8": frames, "params": params, "sensor": sensor, "target": target, "id": vid, "need": need}
+        video = frames.permute(3, 0, 1, 2)                      # nexar_videos.py:441
+        video = self.transform(video) if self.transform else video.float() / 255.0
+        return {"frames": video.permute(1, 2, 3, 0), "sensor": sensor, "target": target, "id": vid}   # :451
 
 
 class GpuVideoDataset(Dataset):
@@ -249,7 +274,11 @@ class GpuVideoDataset(Dataset):
     def __getitem__(self, idx):
         label, vid = self.labels[idx], self.video_ids[idx]
         need = self.fps * self.duration
-        try:
+        if not self.defer and self.transform is not None and _in_dataloader_worker():
+            raise RuntimeError("GpuVideoDataset(defer=False) runs the CUDA transform inside __getitem__, which cannot work "
+                               "in a DataLoader worker process; use defer=True with deferred_collate + GpuAugLoader or "
+                               "num_workers=0")
+        try:   # decode / window failures become the zero clip (ncwv:183-190); transform errors propagate
             reader = self.decoder(self.video_paths[idx])
             n = len(reader)
             ts, vfps = None, 0.0
@@ -270,30 +299,39 @@ class GpuVideoDataset(Dataset):
                 else:
                     frames = np.zeros((need, 720, 1280, 3), np.uint8)
             frames = torch.from_numpy(np.ascontiguousarray(frames[:need]))
-            if self.defer:
-                t = self.transform
-                params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
-                return {"frames_u8": frames, "params": params, "target": label, "id": vid, "need": need}
-            video = frames.permute(3, 0, 1, 2)                  # ncwv:172
-            video = self.transform(video) if self.transform else video.float() / 255.0
-            frames = video.permute(1, 2, 3, 0)                  # ncwv:181
         except Exception:
             if self.defer:
                 return {"frames_u8": None, "params": None, "target": label, "id": vid, "need": need}
             size = (224, 224) if self.transform else (720, 1280)   # ncwv:183-190
-            frames = torch.zeros(need, size[0], size[1], 3)
-        return {"frames": frames, "target": label, "id": vid}
+            return {"frames": torch.zeros(need, size[0], size[1], 3), "target": label, "id": vid}
+        if self.defer:
+            t = self.transform
+            params = t.sample_params(1, frames.shape[1], frames.shape[2])[0] if t is not None else None
+            return {"frames_u8": frames, "params": params, "target": label, "id": vid, "need": need}
+        video = frames.permute(3, 0, 1, 2)                      # ncwv:172
+        video = self.transform(video) if self.transform else video.float() / 255.0
+        return {"frames": video.permute(1, 2, 3, 0), "target": label, "id": vid}   # ncwv:181
 
 
 def deferred_collate(items: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
-    """collate_fn for ``defer=True`` datasets: stacks what stacks, keeps params / failures as lists.  'sensor' is
+    """collate_fn for ``defer=True`` datasets.  The uint8 windows are stacked PER SOURCE RESOLUTION (a batch may mix
+    720p, 1080p and portrait videos: the reference transforms every clip to cs x cs before collation, so it never
+    sees the difference): ``groups`` is a list of ``{'frames_u8': [n,T,H,W,3], 'index': positions in the batch,
+    'params': [...]}``.  Failed items (``frames_u8 is None``) are in no group and become the zero clip.  'sensor' is
     present for the NvidiaDashcamDataset protocol only."""
-    ok = [it["frames_u8"] is not None for it in items]
-    good = [it["frames_u8"] for it, k in zip(items, ok) if k]
+    by_shape: Dict[Any, Dict[str, Any]] = {}
+    for pos, it in enumerate(items):
+        f = it["frames_u8"]
+        if f is None:
+            continue
+        g = by_shape.setdefault(tuple(f.shape), {"frames": [], "index": [], "params": []})
+        g["frames"].append(f)
+        g["index"].append(pos)
+        g["params"].append(it["params"])
     batch = {
-        "frames_u8": torch.stack(good) if good else None,
-        "valid": ok,
-        "params": [it["params"] for it, k in zip(items, ok) if k],
+        "groups": [{"frames_u8": torch.stack(g["frames"]), "index": g["index"], "params": g["params"]}
+                   for g in by_shape.values()],
+        "valid": [it["frames_u8"] is not None for it in items],
         "target": [it["target"] for it in items],
         "id": [it["id"] for it in items],
         "need": items[0].get("need") if items else None,
@@ -304,7 +342,8 @@ def deferred_collate(items: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
 
 
 class GpuAugLoader:
-    """Iterates a DataLoader of deferred batches and runs the fused transform on the device, once per batch."""
+    """Iterates a DataLoader of deferred batches and runs the fused transform on the device: once per batch, or once
+    per source resolution when a batch mixes several."""
 
     def __init__(self, loader: Iterable, transform: GpuVideoTransform, device=None, out_dtype: Optional[torch.dtype] = None):
         self.loader, self.transform = loader, transform
@@ -318,21 +357,25 @@ class GpuAugLoader:
         tf = self.transform
         cs = tf.crop_size
         for batch in self.loader:
-            valid = batch["valid"]
-            n = len(valid)
+            n = len(batch["valid"])
+            groups = batch["groups"]
             out = None
-            if batch["frames_u8"] is not None:
-                u8 = batch["frames_u8"].to(self.device, non_blocking=True)
-                params = batch["params"] if all(p is not None for p in batch["params"]) else None
-                res = tf.forward_batch(u8, params=params, out_dtype=self.out_dtype)       # [b,3,T,cs,cs]
-                if all(valid):
-                    out = res
-                else:   # failed items become the reference's all-zeros clip (nexar_videos.py:479-489)
-                    out = torch.zeros((n,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
-                    out[torch.tensor(valid, device=self.device)] = res
+            if len(groups) == 1 and len(groups[0]["index"]) == n:      # the common case: one resolution, nothing failed
+                g = groups[0]
+                params = g["params"] if all(p is not None for p in g["params"]) else None
+                out = tf.forward_batch(g["frames_u8"].to(self.device, non_blocking=True), params=params,
+                                       out_dtype=self.out_dtype)         # [n,3,T,cs,cs]
             else:
-                t = batch["need"] if batch.get("need") else batch["sensor"].shape[1]
-                out = torch.zeros((n, 3, t, cs, cs), dtype=self.out_dtype or tf.out_dtype, device=self.device)
+                for g in groups:
+                    params = g["params"] if all(p is not None for p in g["params"]) else None
+                    res = tf.forward_batch(g["frames_u8"].to(self.device, non_blocking=True), params=params,
+                                           out_dtype=self.out_dtype)
+                    if out is None:   # failed items stay the reference's all-zeros clip (nexar_videos.py:479-489)
+                        out = torch.zeros((n,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
+                    out[torch.tensor(g["index"], device=self.device)] = res
+                if out is None:
+                    t = batch["need"] if batch.get("need") else batch["sensor"].shape[1]
+                    out = torch.zeros((n, 3, t, cs, cs), dtype=self.out_dtype or tf.out_dtype, device=self.device)
             res_batch = {"frames": out.permute(0, 2, 3, 4, 1), "target": batch["target"], "id": batch["id"]}
             if "sensor" in batch:
                 res_batch["sensor"] = batch["sensor"]
