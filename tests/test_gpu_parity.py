@@ -392,3 +392,87 @@ def test_wide_outputs_with_augmentation_against_oracle(h, w, cs):
     want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": params["flip"], "aug": params["aug"]})
     err = float(np.abs(out - want).max())
     assert err <= TOL_AFTER, err
+
+
+@pytest.mark.parametrize("mode", ["val", "train", "custom"])
+def test_cfg1_sixteen_frame_720p_clip_against_the_reference(mode):
+    """BASELINE.json configs[0] on the device: one 16-frame 1280x720 clip through the reference-compatible call
+    (``tf(video[C,T,H,W])``), same ``random`` seed, against the output the UNMODIFIED reference produced
+    (tests/golden/golden_cfg1_16f.npz: every 5th row / column of every frame + every frame's channel means)."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from vision_collision_detection_b200.synth import make_clip_np
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_cfg1_16f.npz"))
+    kw = {"val": dict(mode="val"), "train": dict(mode="train"),
+          "custom": dict(mode="train", enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+                         contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))}[mode]
+    video = torch.from_numpy(make_clip_np(16, 720, 1280, 101, "dashcam")).permute(3, 0, 1, 2)
+    random.seed(2024)
+    out = _tf(kw)(video.cuda()).float().cpu().numpy()
+    assert out.shape == (3, 16, 224, 224)
+    assert np.abs(out[:, :, ::5, ::5] - g[f"{mode}_sub"]).max() <= TOL_AFTER
+    assert np.abs(out.astype(np.float64).mean(axis=(2, 3)) - g[f"{mode}_mean"]).max() <= 1e-4
+
+
+def test_cfg2_batch_shape_against_the_cpu_port():
+    """The benched shape itself (BASELINE.json configs[1]): 32 clips x 16 x 720p -> 224, 32 DIFFERENT parameter records,
+    bf16 and fp32 outputs of the same launch sequence; three clips of the batch are checked against the CPU port of the
+    reference (oracle/torch_port.py, itself pinned to the reference's outputs), the rest through batch independence:
+    every clip must equal the same clip transformed alone, bit for bit."""
+    from oracle import torch_port as P
+    from vision_collision_detection_b200.synth import make_clip_torch
+    kw = dict(mode="train", enable_custom_augmentation=True, brightness_range=(0.9, 1.1), contrast_range=(0.9, 1.1),
+              saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = _tf(kw)
+    b, t, h, w = 32, 16, 720, 1280
+    clips = torch.stack([make_clip_torch(t, h, w, seed=700 + i, kind="dashcam") for i in range(b)])
+    random.seed(4321)
+    recs = tf.sample_params(b, h, w)
+    assert len({r["flip"] for r in recs}) == 2 and len({r["aug"]["rotation"] for r in recs}) == b
+    out32 = tf.forward_batch(clips, params=recs)
+    out16 = tf.forward_batch(clips, params=recs, out_dtype=torch.bfloat16)
+    assert tuple(out32.shape) == (b, 3, t, 224, 224) and out16.dtype == torch.bfloat16
+    assert torch.equal(out16, out32.to(torch.bfloat16))                      # bf16 = the fp32 result rounded to nearest even
+    cfg = O.TransformConfig(mode="train", crop_size=224, enable_custom_augmentation=True, aug=O.AugConfig(rotation_range=(-5, 5)))
+    for i in (0, 13, 31):
+        want = P.apply_clip_transform(clips[i].cpu().permute(3, 0, 1, 2), cfg, {"flip": recs[i]["flip"], "aug": recs[i]["aug"]}).numpy()
+        err = float(np.abs(out32[i].cpu().numpy() - want).max())
+        assert err <= TOL_AFTER, (i, err)
+    for i in (5, 22):
+        alone = tf.forward_batch(clips[i:i + 1], params=[recs[i]])
+        assert torch.equal(alone[0], out32[i]), i
+
+
+def test_noise_is_fresh_per_call_and_reproducible_per_record():
+    """the noise seed is drawn per clip and call from torch's global generator (the stream the reference's
+    randn_like consumes), never a constant; a parameter record reproduces its own noise."""
+    clip = np.full((2, 96, 160, 3), 128, np.uint8)
+    kw = dict(mode="train", crop_size=64, normalize=False, horizontal_flip_prob=0.0, enable_custom_augmentation=True,
+              brightness_range=(1, 1), contrast_range=(1, 1), saturation_range=(1, 1), hue_range=(0, 0),
+              rotation_range=(0, 0), scale_range=(1, 1), shear_range=(0, 0), translate_range=(0, 0), noise_level=0.05)
+    tf = _tf(kw)
+    x = torch.from_numpy(clip).permute(3, 0, 1, 2)
+    a = tf(x).numpy()
+    rec_a = tf.last_params
+    b = tf(x).numpy()
+    content = (slice(None), slice(None), slice(13, 51), slice(None))
+    da, db = (a - 128 / 255.0)[content], (b - 128 / 255.0)[content]
+    assert abs(float(np.corrcoef(da.ravel(), db.ravel())[0, 1])) < 0.05      # two calls: uncorrelated noise
+    assert rec_a[0]["noise_seed"] != tf.last_params[0]["noise_seed"]
+    frames = torch.from_numpy(clip).cuda().unsqueeze(0)
+    again = tf.forward_batch(frames, params=rec_a)[0].cpu().numpy()
+    assert np.array_equal(again, a)                                          # the record reproduces its noise
+    torch.manual_seed(77)
+    c = tf(x).numpy()
+    torch.manual_seed(77)
+    assert np.array_equal(tf(x).numpy(), c)                                  # torch.manual_seed controls it, as in the reference
+
+
+def test_frame_index_out_of_range_is_refused():
+    tf = _tf(dict(mode="val", crop_size=32))
+    frames = torch.zeros((1, 4, 48, 64, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError, match="frame_index"):
+        tf.forward_batch(frames, frame_index=torch.tensor([[0, 1, 4]]))
+    with pytest.raises(ValueError, match="frame_index"):
+        tf.forward_batch(frames, frame_index=torch.tensor([[-1, 1, 2]]))
+    assert tuple(tf.forward_batch(frames, frame_index=torch.tensor([[3, 3, 0]])).shape) == (1, 3, 3, 32, 32)

@@ -170,3 +170,54 @@ def test_integration_md_ctypes_example_runs():
     assert tuple(got.shape) == (2, 3, 3, 224, 224) and got.dtype == torch.bfloat16
     same = bool(torch.equal(got, want))
     assert same
+
+
+def _decoder_mixed(path):
+    n, seed = map(int, path.split("_"))
+    if n == 0:
+        raise IOError("broken video")
+    h, w = ((96, 160), (72, 128), (160, 96))[seed % 3]        # three source resolutions in one dataset
+    return _FakeReader(n, seed, h, w)
+
+
+def test_loader_with_forked_workers_and_mixed_resolutions():
+    """The trainers' real setting: DataLoader worker PROCESSES (num_workers=2, nexar_train_distributed.py:97) decode and
+    draw the random decisions, nothing in them touches CUDA; batches that mix source resolutions are transformed per
+    resolution.  Every clip must equal the oracle on its own frames with its own draws."""
+    from torch.utils.data import DataLoader
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.videos import GpuAugLoader, GpuDashcamDataset, deferred_collate
+    kw = dict(mode="train", crop_size=56, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = create_video_transforms(**kw)
+    rows = [{"id": f"v{i}", "video_type": "Normal", "path": f"{n}_{i}"} for i, n in enumerate([40, 30, 0, 64, 25, 33])]
+    ds = GpuDashcamDataset(rows, fps=4, duration=3, transform=tf, sample_strategy="center", decoder=_decoder_mixed, defer=True)
+    dl = DataLoader(ds, batch_size=3, shuffle=False, num_workers=2, collate_fn=deferred_collate, pin_memory=True,
+                    multiprocessing_context="fork")
+    # capture what the workers drew: the deferred batches carry the parameter records
+    seen = []
+
+    class Tap:
+        def __iter__(self):
+            for b in dl:
+                seen.append(b)
+                yield b
+
+        def __len__(self):
+            return len(dl)
+
+    out = [b["frames"] for b in GpuAugLoader(Tap(), tf)]
+    assert len(out) == 2 and all(tuple(o.shape) == (3, 12, 56, 56, 3) and o.is_cuda for o in out)
+    cfg = O.TransformConfig(mode="train", crop_size=56, enable_custom_augmentation=True, aug=O.AugConfig(rotation_range=(-5, 5)))
+    checked = 0
+    for bi, b in enumerate(seen):
+        assert sum(len(g["index"]) for g in b["groups"]) == sum(b["valid"]) and len(b["groups"]) >= 2
+        for g in b["groups"]:
+            for k, pos in enumerate(g["index"]):
+                clip = g["frames_u8"][k].numpy()
+                rec = g["params"][k]
+                want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": rec["flip"], "aug": rec["aug"]})
+                got = out[bi][pos].permute(3, 0, 1, 2).float().cpu().numpy()
+                assert float(np.abs(got - want).max()) <= TOL_AFTER
+                checked += 1
+    assert checked == 5 and torch.all(out[0][2] == 0)          # the broken video is the all-zeros clip

@@ -126,3 +126,23 @@ def test_clip_sampler_rules():
     assert len(S.sliding_window_starts(1200, 16, 16)) == 75
     assert len(S.sliding_window_starts(1200, 16, 8)) == 149
     assert len(S.sliding_window_starts(1200, 16, 1)) == 1185
+
+
+@pytest.mark.parametrize("mode", ["val", "train", "custom"])
+def test_cfg1_sixteen_frame_720p_clip(mode):
+    """BASELINE.json configs[0]: one 16-frame 1280x720 clip -> 16 x 224 x 224 through the reference's three live
+    configurations (tests/golden/make_cfg1_golden.py froze the reference's output, sampled every 5th row / column of
+    every frame + every frame's channel means).  The torch port (the timed CPU arm) must reproduce it."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from vision_collision_detection_b200.synth import make_clip_np
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_cfg1_16f.npz"))
+    clip = torch.from_numpy(make_clip_np(16, 720, 1280, 101, "dashcam")).permute(3, 0, 1, 2)
+    aug = O.AugConfig(rotation_range=(-5, 5)) if mode == "custom" else O.AugConfig()
+    cfg = O.TransformConfig(mode="val" if mode == "val" else "train", crop_size=224,
+                            enable_custom_augmentation=(mode == "custom"), aug=aug)
+    random.seed(2024)
+    out = P.clip_transform(clip, cfg, random).numpy()
+    assert out.shape == (3, 16, 224, 224)
+    assert np.abs(out[:, :, ::5, ::5] - g[f"{mode}_sub"]).max() <= 1e-5
+    assert np.abs(out.astype(np.float64).mean(axis=(2, 3)) - g[f"{mode}_mean"]).max() <= 1e-6
