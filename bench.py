@@ -384,6 +384,9 @@ def main():
     if os.environ.get("NEXAR_FAST_BANDS"):
         from vision_collision_detection_b200 import _lib as _l
         _l.lib().nexar_set_fast_bands(int(os.environ["NEXAR_FAST_BANDS"]))
+    if os.environ.get("NEXAR_CHUNK_CLIPS"):
+        from vision_collision_detection_b200 import _lib as _l
+        _l.lib().nexar_set_chunk_clips(int(os.environ["NEXAR_CHUNK_CLIPS"]))
     if os.environ.get("NEXAR_RESIZE_VARIANT"):      # experiments: 2 = the unfused K1 + K1.5 + K2 + K3 path
         from vision_collision_detection_b200 import _lib as _l
         _l.lib().nexar_set_resize_kernel(int(os.environ["NEXAR_RESIZE_VARIANT"]))
@@ -423,7 +426,7 @@ def main():
         step(i)
     barrier()
     from vision_collision_detection_b200 import _lib
-    _lib.lib().nexar_profile_begin(args.steps + 8)
+    _lib.lib().nexar_profile_begin(64 * args.steps + 8)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
@@ -508,7 +511,7 @@ def main():
         # dominant kernel: resize_fast_kernel.  With augmentation it is the fused cluster kernel (resize + colour + affine +
         # normalise + store = the whole transform of the batch); without, the resize + normalise + store kernel.  Either way
         # its algorithmic bytes are the step's: source read once + output written once.
-        k_ms = (sum(k1_ms) / len(k1_ms)) if k1_ms else None
+        k_ms = (sum(k1_ms) / args.steps) if k1_ms else None   # per step: the sum over the chunks of a step
         kern = None
         if k_ms:
             k_ach = step_bytes / (k_ms * 1e-3) / 1e9

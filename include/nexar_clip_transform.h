@@ -159,6 +159,13 @@ int nexar_profile_end(float* ms_out, int32_t cap);
  * row bands each frame is split into by the fast kernel (0 = auto). */
 int nexar_set_resize_kernel(int32_t variant);
 int nexar_set_fast_bands(int32_t bands);
+/* Geometry (affine gather) kernel: 0 = auto (the kernel specialised for the 720p -> 224 / -> 320 letterboxes writing a
+ * planar row-contiguous tensor when the call has that shape), 1 = always the general kernel. */
+int nexar_set_geometry_kernel(int32_t variant);
+/* Experiment: process an augmented batch in chunks of `clips` whole clips (resize, colour and geometry kernels of one
+ * chunk back to back, for L2 locality of the intermediate); 0 = the whole batch at once (default: measured faster on
+ * B200 at every batch size tried).  The result does not depend on it. */
+int nexar_set_chunk_clips(int32_t clips);
 
 #ifdef __cplusplus
 }

@@ -476,3 +476,67 @@ def test_frame_index_out_of_range_is_refused():
     with pytest.raises(ValueError, match="frame_index"):
         tf.forward_batch(frames, frame_index=torch.tensor([[-1, 1, 2]]))
     assert tuple(tf.forward_batch(frames, frame_index=torch.tensor([[3, 3, 0]])).shape) == (1, 3, 3, 32, 32)
+
+
+@pytest.mark.parametrize("cs,t", [(224, 3), (224, 9), (320, 2)])
+def test_specialised_and_general_geometry_kernels_agree(cs, t):
+    """720p -> 224 / 320 letterboxes writing a planar tensor take geometry_spec_kernel (compile-time frame sizes, one
+    pointer per pixel, clamped 2 x 2 window, packed fp32 blend); everything else the general geometry_kernel.  Both
+    must give the same pixels, for the live call site's parameters and for extreme ones (the whole canvas becomes
+    boundary tiles), with and without the point effects, in fp32 and bf16, and both must match the oracle."""
+    from vision_collision_detection_b200 import _lib
+    from vision_collision_detection_b200.synth import make_clip_np
+    clip = make_clip_np(t, 720, 1280, 700 + cs + t, "dashcam")
+    kw = dict(mode="train", crop_size=cs, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = _tf(kw)
+    random.seed(31 * cs + t)
+    live = tf.sample_params(1, 720, 1280)[0]
+    wild = dict(brightness=1.4, contrast=0.6, saturation=1.7, hue=0.31, rotation=133.0, scale=0.6, shear=21.0,
+                translate_x=37.0, translate_y=-55.5, apply_affine=True, apply_grayscale=False, apply_noise=False,
+                apply_blur=False, apply_cutout=False, apply_color_inversion=True, apply_solarization=True,
+                apply_posterization=False)
+    zoom = dict(wild, rotation=-4.0, scale=2.2, shear=0.0, translate_x=-9.0, translate_y=3.0,
+                apply_color_inversion=False, apply_solarization=False)
+    ident = dict(wild, brightness=1.0, contrast=1.0, saturation=1.0, hue=0.0, rotation=0.0, scale=1.0, shear=0.0,
+                 translate_x=0.0, translate_y=0.0, apply_affine=False, apply_color_inversion=False, apply_solarization=False)
+    cfg = O.TransformConfig(mode="train", crop_size=cs, enable_custom_augmentation=True, aug=O.AugConfig(
+        brightness_range=(0.9, 1.1), contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5)))
+    L = _lib.lib()
+    for k, params in enumerate([live, {"flip": True, "aug": wild}, {"flip": False, "aug": zoom}, {"flip": True, "aug": ident}]):
+        outs = {}
+        try:
+            for variant in (0, 1):
+                L.nexar_set_geometry_kernel(variant)
+                outs[variant] = _run(tf, clip, params)
+                outs[variant, "bf16"] = _run(_tf(kw, out_dtype=torch.bfloat16), clip, params)
+        finally:
+            L.nexar_set_geometry_kernel(0)
+        assert np.abs(outs[0] - outs[1]).max() <= 2e-6, k        # same formulas; one fused multiply-add differs
+        assert np.abs(outs[0, "bf16"] - outs[1, "bf16"]).max() <= 2.0 ** -6, k   # at most one bf16 ulp at |v| < 4
+        want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": params["flip"], "aug": params["aug"]})
+        err = float(np.abs(outs[0] - want).max())
+        assert err <= TOL_AFTER, (k, err)
+
+
+def test_result_does_not_depend_on_the_chunking():
+    """nexar_set_chunk_clips processes a batch in groups of whole clips with separate workspace slices: bit-identical."""
+    from vision_collision_detection_b200 import _lib
+    from vision_collision_detection_b200.synth import make_clip_np
+    kw = dict(mode="train", crop_size=224, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = _tf(kw, out_dtype=torch.bfloat16)
+    frames = torch.from_numpy(np.stack([make_clip_np(3, 720, 1280, 40 + i, "dashcam") for i in range(5)])).cuda()
+    frames[3] = frames[3] & 1                       # one clip whose maximum is 1: the fix-up path inside a chunk
+    random.seed(77)
+    params = tf.sample_params(5, 720, 1280)
+    L = _lib.lib()
+    outs = []
+    try:
+        for chunk in (0, 1, 2, 4):
+            L.nexar_set_chunk_clips(chunk)
+            outs.append(tf.forward_batch(frames, params=params).float().cpu().numpy())
+    finally:
+        L.nexar_set_chunk_clips(0)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])

@@ -119,6 +119,8 @@ def lib():
     L.nexar_last_launch_count.restype = C.c_int
     L.nexar_set_resize_kernel.argtypes = [C.c_int32]
     L.nexar_set_fast_bands.argtypes = [C.c_int32]
+    L.nexar_set_geometry_kernel.argtypes = [C.c_int32]
+    L.nexar_set_chunk_clips.argtypes = [C.c_int32]
     L.nexar_profile_begin.argtypes = [C.c_int32]
     L.nexar_profile_end.argtypes = [C.c_void_p, C.c_int32]
     if L.nexar_abi_version() != NEXAR_ABI_VERSION:
@@ -157,7 +159,7 @@ def aa_taps(in_size: int, out_size: int, cap: int = 64):
     return start, count, wts[:, :k.value].copy()
 
 
-def profile_end(cap: int = 4096):
+def profile_end(cap: int = 1 << 16):
     """-> list of per-call durations (ms) of the resize kernel since nexar_profile_begin."""
     buf = np.zeros(cap, np.float32)
     n = lib().nexar_profile_end(buf.ctypes.data, cap)

@@ -30,6 +30,8 @@ static thread_local int g_launches = 0;
 // experiment knobs and the optional kernel timing are per calling thread (the library keeps no process-global mutable state)
 static thread_local int g_resize_variant = 0;  // 0 auto, 1 force the general fp32 kernels, 4 fused cluster kernel for augmented batches
 static thread_local int g_fast_bands = 0;      // 0 auto
+static thread_local int g_chunk_clips = 0;     // clips per chunk of an augmented batch (0 auto)
+static thread_local int g_geo_variant = 0;     // 0 auto (specialised geometry kernel when the shape allows it), 1 force the general one
 
 static thread_local std::vector<cudaEvent_t> g_prof_ev;
 static thread_local int g_prof_n = 0;
@@ -230,6 +232,14 @@ extern "C" int nexar_set_fast_bands(int32_t n) {
   g_fast_bands = n;
   return NEXAR_OK;
 }
+extern "C" int nexar_set_chunk_clips(int32_t n) {
+  g_chunk_clips = n;
+  return NEXAR_OK;
+}
+extern "C" int nexar_set_geometry_kernel(int32_t v) {
+  g_geo_variant = v;
+  return NEXAR_OK;
+}
 
 extern "C" int nexar_profile_begin(int32_t max_calls) {
   for (cudaEvent_t e : g_prof_ev) cudaEventDestroy(e);
@@ -404,6 +414,7 @@ static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
 static const int kMaxBands = 16;
+
 
 // Per-frame constants computed once by K1.5 (frame_stats_kernel) so that K2/K3 start with a few 16-byte loads
 // instead of re-deriving the content box, the colour parameters and the pad colour in every thread.
@@ -817,11 +828,6 @@ __device__ __forceinline__ uint2 pack_q21(float r, float g, float b) {
   const unsigned qb = __float_as_uint(fmaf(b, kQ21, 8388608.0f)) & 0x1FFFFFu;
   return make_uint2(qr | (qg << 21), (qg >> 11) | (qb << 10));
 }
-__device__ __forceinline__ void unpack_q21(uint2 v, float& r, float& g, float& b) {
-  r = (float)(v.x & 0x1FFFFFu) * kQ21Inv;
-  g = (float)(__funnelshift_r(v.x, v.y, 21) & 0x1FFFFFu) * kQ21Inv;
-  b = (float)((v.y >> 10) & 0x1FFFFFu) * kQ21Inv;
-}
 constexpr float kQ15 = 32767.0f;
 constexpr float kQ15Magic = 8388608.0f + 32768.0f;  // low 16 bits of float_bits(v * 32767 + magic) = 0x8000 | round(v * 32767)
 constexpr float kQ15Inv = 32768.0f / 32767.0f;      // v = (F - 1) * kQ15Inv
@@ -1139,10 +1145,27 @@ struct ColourParams {
 // which is _hsv2rgb's (v, q, p, p, t, v) table with v * s = cr = maxc - minc (tv:_functional_tensor.py:258-321).
 // hue == 0: torchvision still runs RGB -> HSV -> RGB, which is the identity up to a few ulp; it is skipped (uniform per
 // frame).  Measured against the oracle, which always runs it: < 1e-6.
+__device__ __forceinline__ void colour_chain_tail(float& r, float& g, float& b, const ColourParams& c);
 __device__ __forceinline__ void colour_chain(float& r, float& g, float& b, const ColourParams& c) {
   r = __saturatef(fmaf(c.contrast, r, c.cmean));
   g = __saturatef(fmaf(c.contrast, g, c.cmean));
   b = __saturatef(fmaf(c.contrast, b, c.cmean));
+  colour_chain_tail(r, g, b, c);
+}
+// The same chain on a packed stage-1 pixel.  The three 21-bit fields are OR-ed into the mantissa of 2^23 (one logic
+// operation each, no integer-to-float conversion): F = 2^23 + q, and the contrast blend absorbs both the scale and the
+// offset: contrast * q / (2^21 - 1) + cmean = F * cq + (cmean - cq * 2^23), cq = contrast / (2^21 - 1).
+__device__ __forceinline__ void colour_chain_q21(uint2 v, float& r, float& g, float& b, const ColourParams& c) {
+  const float fr = __uint_as_float((v.x & 0x1FFFFFu) | 0x4B000000u);
+  const float fg = __uint_as_float((__funnelshift_r(v.x, v.y, 21) & 0x1FFFFFu) | 0x4B000000u);
+  const float fb = __uint_as_float((v.y >> 10) | 0x4B000000u);   // bit 31 of a stage-1 pixel is zero
+  const float cq = c.contrast * kQ21Inv, c0 = fmaf(-cq, 8388608.0f, c.cmean);
+  r = __saturatef(fmaf(fr, cq, c0));
+  g = __saturatef(fmaf(fg, cq, c0));
+  b = __saturatef(fmaf(fb, cq, c0));
+  colour_chain_tail(r, g, b, c);
+}
+__device__ __forceinline__ void colour_chain_tail(float& r, float& g, float& b, const ColourParams& c) {
   const float gq = c.saturation_q * fmaf(0.114f, b, fmaf(0.587f, g, 0.2989f * r));
   r = __saturatef(fmaf(c.saturation, r, gq));
   g = __saturatef(fmaf(c.saturation, g, gq));
@@ -1235,8 +1258,7 @@ __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __gri
   for (int k = 0; k < kColourPerThread; ++k)
     if (i0 + k * 256 < n) {
       float r, g, b;
-      unpack_q21(v[k], r, g, b);
-      colour_chain(r, g, b, c);
+      colour_chain_q21(v[k], r, g, b, c);
       base[i0 + k * 256] = pack_q15(r, g, b);
     }
 }
@@ -1374,8 +1396,7 @@ __device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KA
         for (int k = 0; k < U; ++k)
           if (e0 + k * NT < n) {
             float r, g, b;
-            unpack_q21(v[k], r, g, b);
-            colour_chain(r, g, b, c);
+            colour_chain_q21(v[k], r, g, b, c);
             rows[e0 + k * NT] = pack_q15(r, g, b);
           }
       }
@@ -1385,8 +1406,7 @@ __device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KA
           uint2* q = rows + row * A.bw + col;
           const uint2 v = *q;
           float r, g, b;
-          unpack_q21(v, r, g, b);
-          colour_chain(r, g, b, c);
+          colour_chain_q21(v, r, g, b, c);
           *q = pack_q15(r, g, b);
         }
     }
@@ -1813,6 +1833,272 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
   }
 }
 
+// K3, specialised.  The intermediate frame size (BH x BW), the canvas (CS) and a planar, row-contiguous destination
+// (x stride 1, y stride CS, frame stride CS * CS) are compile-time constants, so that
+//   * a pixel needs ONE 64-bit source pointer per lane pixel: its four bilinear neighbours sit at the immediate offsets
+//     {0, 1, BW, BW + 1} pixels and frame f of the group at f * BH * BW pixels (every load is [pointer + immediate]);
+//     at the edges of the content box the base is clamped into the box and the weights are re-assigned to the two
+//     loaded columns / rows (a neighbour that is pad or outside the canvas keeps weight zero), so the boundary tiles
+//     use the same addressing as the interior ones;
+//   * a channel of the output needs one pointer too (frame f at f * CS * CS elements);
+//   * the geometry of a pixel is shared by NF (8) frames of the clip instead of 4;
+//   * the blend runs on packed fp32 pairs (FFMA2: the two pixels of a lane, channel by channel) and the interior
+//     class folds the q15 scale and the normalisation into one multiply-add per channel.
+// Same formulas and the same per-pixel operation order as geometry_kernel, which stays the general fallback.
+#ifndef NEXAR_GEO2_FRAMES
+#define NEXAR_GEO2_FRAMES 8
+#endif
+#ifndef NEXAR_GEO2_MINB
+#define NEXAR_GEO2_MINB 3
+#endif
+#ifndef NEXAR_GEO2_WARPS
+#define NEXAR_GEO2_WARPS 8   // warps per CTA: the CTA tile is 32 x (4 * warps) pixels
+#endif
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#ifndef NEXAR_GEO2_EXP
+#define NEXAR_GEO2_EXP 0
+#endif
+#if NEXAR_GEO2_EXP & 2   /* timing experiment: no loads */
+__device__ __forceinline__ uint2 ldg_u2(const uint2* p) { return make_uint2((unsigned)(size_t)p, (unsigned)((size_t)p >> 3)); }
+#else
+__device__ __forceinline__ uint2 ldg_u2(const uint2* p) { return __ldg(p); }
+#endif
+__device__ __forceinline__ void l2_prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef NEXAR_GEO2_L2PF
+#define NEXAR_GEO2_L2PF 1   // first frame of the group whose rows are prefetched into L2 at the start of a pass (0: off)
+#endif
+
+template <typename DstT, bool TAIL, int BH, int BW, int CS>
+__global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geometry_spec_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  static_assert(BH >= 2 && BW >= 2, "the clamped 2 x 2 window needs a 2 x 2 box");
+  constexpr int NF = NEXAR_GEO2_FRAMES;
+  constexpr int FPX = BH * BW;   // pixels of one intermediate frame
+  constexpr int OPX = CS * CS;   // elements of one output plane
+  const int ngroup = (A.T + NF - 1) / NF;
+  const int clip = blockIdx.z / ngroup;
+  const int t0 = (blockIdx.z - clip * ngroup) * NF;
+  const int nfr = min(NF, A.T - t0);
+  const int frame0 = clip * A.T + t0;
+  const float4* fi4 = (const float4*)(A.finfo + frame0);
+  const float4 q3 = __ldg(fi4 + 3);
+  const unsigned flags = __float_as_uint(q3.z);
+  if (!(flags & NEXAR_AUG)) return;
+  if (A.pass == 4 && A.clip_max[clip] == 0u) return;  // fixup_frame_kernel finishes those clips on its own
+  // Warp tile = 32 x 4 output pixels.  A lane owns ONE column and two vertically adjacent pixels per pass (two passes):
+  // the 32 lanes of a load read 32 consecutive 8-byte pixels of one source row (two or three 128-byte lines) and the
+  // 32 lanes of a store write 32 consecutive elements, which halves the L1 wavefronts of a two-pixels-per-lane row layout.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx0 = blockIdx.x * 32, ty0 = (blockIdx.y * NEXAR_GEO2_WARPS + warp) * 4;
+  const int x = tx0 + lane;
+  if (ty0 >= CS) return;
+  const float4 q2 = __ldg(fi4 + 2);
+  const int4 bx = __ldg((const int4*)fi4 + 1);
+  const NexarClipParams* cp = A.params + clip;   // only the rare tail effects read it
+  const int by0 = bx.x, by1 = bx.y, bx0 = bx.z, bx1 = bx.w;
+  constexpr float half = (float)CS * 0.5f, fcs = (float)CS;
+  const bool affine = (flags & NEXAR_AFFINE) != 0u;
+  const float g0 = q2.x, g1 = q2.y, g2 = q2.z, g3 = q2.w, g4 = q3.x, g5 = q3.y;
+  int cls = GEO_GENERAL;
+  if (affine) {  // tile class, as in geometry_kernel (tile = 32 x 4 pixels)
+    const float xc = (float)(tx0 + 16) - half, yc = (float)(ty0 + 2) - half;
+    const float sxc = fmaf(fmaf(yc, g1, xc * g0) + g2 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float syc = fmaf(fmaf(yc, g4, xc * g3) + g5 + 1.0f, fcs, -1.0f) * 0.5f;
+    const float ex = (15.5f * fabsf(g0) + 1.5f * fabsf(g1)) * half + 0.01f;
+    const float ey = (15.5f * fabsf(g3) + 1.5f * fabsf(g4)) * half + 0.01f;
+    const float xmin = sxc - ex, xmax = sxc + ex, ymin = syc - ey, ymax = syc + ey;
+    const float fby0 = (float)by0, fby1 = (float)by1, fbx0 = (float)bx0, fbx1 = (float)bx1;
+    const bool inside = xmin >= 0.0f && xmax <= fcs - 1.0f && ymin >= 0.0f && ymax <= fcs - 1.0f;
+    const bool outside_box = ymax + 1.0f < fby0 || ymin >= fby1 || xmax + 1.0f < fbx0 || xmin >= fbx1;
+    const bool interior = xmin >= fbx0 && xmax <= fbx1 - 1.0f && ymin >= fby0 && ymax <= fby1 - 1.0f;
+    cls = (inside && outside_box) ? GEO_FILL : interior ? GEO_INTERIOR : GEO_GENERAL;
+  }
+  if (x >= CS) return;
+  const uint2* const fr0 = A.inter + ((int64_t)frame0 * FPX - (by0 * BW + bx0));  // frame t0, indexed by canvas (y, x)
+  DstT* const ob0 = (DstT*)A.dst + ((int64_t)clip * A.sb + (int64_t)t0 * OPX);
+  const int64_t osc = A.sc;
+  const bool tail_fx = TAIL && (flags & kTailFlags) != 0u;
+  const float nsr = A.nscale[0], nsg = A.nscale[1], nsb = A.nscale[2], nbr = A.nbias[0], nbg = A.nbias[1], nbb = A.nbias[2];
+  // interior class: out = s * (k * ns) + (nb - k * ns), s = sum(w * F), F = 1 + q / 32768, k = 32768 / 32767
+  const float kir = kQ15Inv * nsr, kig = kQ15Inv * nsg, kib = kQ15Inv * nsb;
+  const float cir = nbr - kir, cig = nbg - kig, cib = nbb - kib;
+  const float xb = (float)x - half + 0.5f;
+  const float xg0 = xb * g0, xg3 = xb * g3;
+
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int y = ty0 + 2 * pass;        // this lane's pixels: (x, y) and (x, y + 1)
+    if (y >= CS) break;
+    const bool has2 = y + 1 < CS;
+    // ---- geometry of this lane's two pixels, shared by the frames of the group ----
+    int o[2] = {0, 0};
+    float2 w00 = {0.f, 0.f}, w01 = {0.f, 0.f}, w10 = {0.f, 0.f}, w11 = {0.f, 0.f};
+    float mq[2] = {1.0f, 1.0f}, t0q[2] = {0.f, 0.f}, pmq[2] = {0.f, 0.f};
+    if (cls != GEO_FILL) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ye = has2 ? y + e : y;
+        const float yb = (float)ye - half + 0.5f;
+        float wx0, wx1, wy0, wy1, x0f, y0f;
+        if (affine) {
+          // tv _gen_affine_grid + grid_sample(bilinear, zeros, align_corners=False) on [img | ones], img * mask
+          const float gx = fmaf(yb, g1, xg0) + g2;
+          const float gy = fmaf(yb, g4, xg3) + g5;
+          const float ix = fmaf(gx + 1.0f, fcs, -1.0f) * 0.5f;
+          const float iy = fmaf(gy + 1.0f, fcs, -1.0f) * 0.5f;
+          x0f = floorf(ix); y0f = floorf(iy);
+          wx1 = ix - x0f; wy1 = iy - y0f;
+          wx0 = 1.0f - wx1; wy0 = 1.0f - wy1;
+        } else {  // no affine: the pixel itself
+          x0f = (float)x; y0f = (float)ye;
+          wx1 = wy1 = 0.0f; wx0 = wy0 = 1.0f;
+        }
+        float a00, a01, a10, a11;
+        if (cls == GEO_INTERIOR) {
+          o[e] = (int)y0f * BW + (int)x0f;
+          a00 = wx0 * wy0; a01 = wx1 * wy0; a10 = wx0 * wy1; a11 = wx1 * wy1;
+        } else {
+          // clamp before the int cast so wild matrices cannot overflow
+          const int x0 = (int)fminf(fmaxf(x0f, -2.0f), fcs + 1.0f);
+          const int yq = (int)fminf(fmaxf(y0f, -2.0f), fcs + 1.0f);
+          const bool inx0 = (unsigned)x0 < (unsigned)CS, inx1 = (unsigned)(x0 + 1) < (unsigned)CS;
+          const bool iny0 = (unsigned)yq < (unsigned)CS, iny1 = (unsigned)(yq + 1) < (unsigned)CS;
+          const float ax0 = inx0 ? wx0 : 0.0f, ax1 = inx1 ? wx1 : 0.0f, ay0 = iny0 ? wy0 : 0.0f, ay1 = iny1 ? wy1 : 0.0f;
+          const float m = (ax0 + ax1) * (ay0 + ay1);               // interpolated ones-mask
+          const bool cx0 = x0 >= bx0 && x0 < bx1, cx1 = x0 + 1 >= bx0 && x0 + 1 < bx1;
+          const bool cy0 = yq >= by0 && yq < by1, cy1 = yq + 1 >= by0 && yq + 1 < by1;
+          const float bx0w = cx0 ? wx0 : 0.0f, bx1w = cx1 ? wx1 : 0.0f, by0w = cy0 ? wy0 : 0.0f, by1w = cy1 ? wy1 : 0.0f;
+          // the loaded 2 x 2 window starts at (xc, yc), clamped into the box; each loaded column / row takes the weight
+          // of the neighbour it coincides with (none: zero)
+          const int xc = min(max(x0, bx0), bx1 - 2), yc = min(max(yq, by0), by1 - 2);
+          const int dx = xc - x0, dy = yc - yq;
+          const float wA = dx == 0 ? bx0w : dx == 1 ? bx1w : 0.0f, wB = dx == 0 ? bx1w : dx == -1 ? bx0w : 0.0f;
+          const float hA = dy == 0 ? by0w : dy == 1 ? by1w : 0.0f, hB = dy == 0 ? by1w : dy == -1 ? by0w : 0.0f;
+          o[e] = yc * BW + xc;
+          a00 = wA * hA; a01 = wB * hA; a10 = wA * hB; a11 = wB * hB;
+          const float wc = (bx0w + bx1w) * (by0w + by1w);
+          mq[e] = m;
+          t0q[e] = -kQ15Inv * wc;
+          pmq[e] = m - wc;
+        }
+        if (e == 0) { w00.x = a00; w01.x = a01; w10.x = a10; w11.x = a11; }
+        else        { w00.y = a00; w01.y = a01; w10.y = a10; w11.y = a11; }
+      }
+    }
+    const uint2* const pa = fr0 + o[0];
+    const uint2* const pb = fr0 + o[1];
+    DstT* const por = ob0 + (y * CS + x);
+    DstT* const pog = por + osc;
+    DstT* const pob = pog + osc;
+    auto put = [&](DstT* p, int f, float va, float vb) {   // one channel of the lane's two pixels, frame f of the group
+#if NEXAR_GEO2_EXP & 1   /* timing experiment: no stores (unless NaN, to keep the arithmetic alive) */
+      if (va != va || vb != vb)
+#endif
+      {
+      store_out_global<DstT>(p + f * OPX, va);
+      if (has2) store_out_global<DstT>(p + (f * OPX + CS), vb);
+      }
+    };
+    // ---- the frames of the group (fully unrolled: every address below is [pointer + immediate]); the eight neighbour
+    // loads of frame f + 1 are issued before frame f is blended ----
+    uint2 va[2][4], vb[2][4];
+    if (cls != GEO_FILL) {
+#if NEXAR_GEO2_L2PF
+      // pull the three source rows this lane needs from the LATER frames of the group into L2 now (the intermediate of a
+      // whole batch does not stay L2-resident behind the 1.4 GB source stream): their loads then find an L2 hit
+#pragma unroll
+      for (int f = NEXAR_GEO2_L2PF; f < NF; ++f)
+        if (f < nfr) {
+          l2_prefetch_line(pa + f * FPX);
+          l2_prefetch_line(pa + f * FPX + BW);
+          l2_prefetch_line(pb + f * FPX + BW);
+        }
+#endif
+      va[0][0] = ldg_u2(pa); va[0][1] = ldg_u2(pa + 1); va[0][2] = ldg_u2(pa + BW); va[0][3] = ldg_u2(pa + BW + 1);
+      vb[0][0] = ldg_u2(pb); vb[0][1] = ldg_u2(pb + 1); vb[0][2] = ldg_u2(pb + BW); vb[0][3] = ldg_u2(pb + BW + 1);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      if (f >= nfr) break;
+      const float4 padv = __ldg(fi4 + 5 * f);  // FrameInfo is five float4; the pad colour comes first
+      float2 rr = {padv.x, padv.x}, gg = {padv.y, padv.y}, bb = {padv.z, padv.z};
+      if (cls != GEO_FILL) {
+        if (f + 1 < NF && f + 1 < nfr) {
+          const uint2* qa = pa + (f + 1) * FPX;
+          const uint2* qb = pb + (f + 1) * FPX;
+          uint2* na = va[(f + 1) & 1];
+          uint2* nb = vb[(f + 1) & 1];
+          na[0] = ldg_u2(qa); na[1] = ldg_u2(qa + 1); na[2] = ldg_u2(qa + BW); na[3] = ldg_u2(qa + BW + 1);
+          nb[0] = ldg_u2(qb); nb[1] = ldg_u2(qb + 1); nb[2] = ldg_u2(qb + BW); nb[3] = ldg_u2(qb + BW + 1);
+        }
+        const uint2* ca = va[f & 1];
+        const uint2* cb = vb[f & 1];
+        float2 sr = fmul2(make_float2(q15_r(ca[0]), q15_r(cb[0])), w00);
+        float2 sg = fmul2(make_float2(q15_g(ca[0]), q15_g(cb[0])), w00);
+        float2 sb = fmul2(make_float2(q15_b(ca[0]), q15_b(cb[0])), w00);
+        sr = ffma2(make_float2(q15_r(ca[1]), q15_r(cb[1])), w01, sr);
+        sg = ffma2(make_float2(q15_g(ca[1]), q15_g(cb[1])), w01, sg);
+        sb = ffma2(make_float2(q15_b(ca[1]), q15_b(cb[1])), w01, sb);
+        sr = ffma2(make_float2(q15_r(ca[2]), q15_r(cb[2])), w10, sr);
+        sg = ffma2(make_float2(q15_g(ca[2]), q15_g(cb[2])), w10, sg);
+        sb = ffma2(make_float2(q15_b(ca[2]), q15_b(cb[2])), w10, sb);
+        sr = ffma2(make_float2(q15_r(ca[3]), q15_r(cb[3])), w11, sr);
+        sg = ffma2(make_float2(q15_g(ca[3]), q15_g(cb[3])), w11, sg);
+        sb = ffma2(make_float2(q15_b(ca[3]), q15_b(cb[3])), w11, sb);
+        if (cls == GEO_INTERIOR) {  // m = wc = 1
+          if (!tail_fx) {           // scale and normalisation in one multiply-add
+            put(por, f, fmaf(sr.x, kir, cir), fmaf(sr.y, kir, cir));
+            put(pog, f, fmaf(sg.x, kig, cig), fmaf(sg.y, kig, cig));
+            put(pob, f, fmaf(sb.x, kib, cib), fmaf(sb.y, kib, cib));
+            continue;
+          }
+          rr = make_float2(fmaf(sr.x, kQ15Inv, -kQ15Inv), fmaf(sr.y, kQ15Inv, -kQ15Inv));
+          gg = make_float2(fmaf(sg.x, kQ15Inv, -kQ15Inv), fmaf(sg.y, kQ15Inv, -kQ15Inv));
+          bb = make_float2(fmaf(sb.x, kQ15Inv, -kQ15Inv), fmaf(sb.y, kQ15Inv, -kQ15Inv));
+        } else {
+          rr = make_float2(mq[0] * fmaf(sr.x, kQ15Inv, fmaf(padv.x, pmq[0], t0q[0])), mq[1] * fmaf(sr.y, kQ15Inv, fmaf(padv.x, pmq[1], t0q[1])));
+          gg = make_float2(mq[0] * fmaf(sg.x, kQ15Inv, fmaf(padv.y, pmq[0], t0q[0])), mq[1] * fmaf(sg.y, kQ15Inv, fmaf(padv.y, pmq[1], t0q[1])));
+          bb = make_float2(mq[0] * fmaf(sb.x, kQ15Inv, fmaf(padv.z, pmq[0], t0q[0])), mq[1] * fmaf(sb.y, kQ15Inv, fmaf(padv.z, pmq[1], t0q[1])));
+        }
+      }
+      if (tail_fx) {
+        const int frame = frame0 + f;
+        float rv[2] = {rr.x, rr.y}, gv[2] = {gg.x, gg.y}, bv[2] = {bb.x, bb.y};
+        bool to_canvas = false;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (e == 1 && !has2) break;
+          const int idx = (y + e) * CS + x;
+          float r = rv[e], g = gv[e], b = bv[e];
+          if (flags & NEXAR_GRAYSCALE) r = g = b = gray_of(r, g, b);
+          if (flags & NEXAR_NOISE) {
+            const unsigned base = (unsigned)((frame * 3) * CS * CS + idx);
+            r = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base), cp->noise_level, r));
+            g = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + CS * CS), cp->noise_level, g));
+            b = clamp01(fmaf(gauss_noise(cp->noise_seed[0], cp->noise_seed[1], base + 2 * CS * CS), cp->noise_level, b));
+          }
+          if (flags & NEXAR_BLUR) {  // the blur kernel finishes the chain from the planar canvas
+            float* cv = A.canvas + (size_t)frame * 3 * CS * CS;
+            cv[idx] = r;
+            cv[CS * CS + idx] = g;
+            cv[2 * CS * CS + idx] = b;
+            to_canvas = true;
+            continue;
+          }
+          point_effects(r, g, b, cp, flags, y + e, x);
+          rv[e] = r; gv[e] = g; bv[e] = b;
+        }
+        if (to_canvas) continue;
+        rr = make_float2(rv[0], rv[1]); gg = make_float2(gv[0], gv[1]); bb = make_float2(bv[0], bv[1]);
+      }
+      // nscale / nbias are 1 / 0 when the output is not normalised
+      put(por, f, fmaf(rr.x, nsr, nbr), fmaf(rr.y, nsr, nbr));
+      put(pog, f, fmaf(gg.x, nsg, nbg), fmaf(gg.y, nsg, nbg));
+      put(pob, f, fmaf(bb.x, nsb, nbb), fmaf(bb.y, nsb, nbb));
+    }
+  }
+}
+
 // K4: gaussian blur (tv gaussian_blur: reflect pad, outer-product kernel) + rest of the chain.
 template <typename DstT>
 __global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
@@ -1894,13 +2180,13 @@ static cudaError_t launch_fast(Kern kern, dim3 grid, int nt, size_t smem, cudaSt
 }
 
 template <typename SrcT, typename DstT>
-static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K, int aug_mode, int blur_mode) {
+static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K, int n_clips, int aug_mode, int blur_mode) {
   cudaStream_t st = (cudaStream_t)a->stream;
   const int nf = K.n_frames;
   const DevPlan& P = p->d;
   const bool covers_source = (p->g.off_y >= 0 && p->g.off_x >= 0 && p->g.off_y + p->g.resize_h <= p->g.canvas &&
                               p->g.off_x + p->g.resize_w <= p->g.canvas);
-  CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, ((size_t)a->n_clips + nf) * sizeof(unsigned), st));
+  CUDA_TRY(cudaMemsetAsync(K.clip_max, 0, ((size_t)n_clips + nf) * sizeof(unsigned), st));
   const int vis_rows = imin(p->g.resize_h, p->g.canvas);
   const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
   const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
@@ -1914,11 +2200,26 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
       ++g_launches;
     }
     colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
-    const dim3 ggrid((cs + 31) / 32, (cs + 16 * kGeoPasses - 1) / (16 * kGeoPasses), a->n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
-    if (a->any_flags & kTailFlags)
-      geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
-    else
-      geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
+    // the two production geometries (720p -> 224 and 720p / 1080p -> 320 letterboxes) writing a planar row-contiguous
+    // tensor take the specialised kernel; everything else the general one
+    const bool planar = K.sx == 1 && K.sy == cs && K.st == (int64_t)cs * cs && g_geo_variant != 1;
+    const bool tail = (a->any_flags & kTailFlags) != 0;
+    const dim3 sgrid((cs + 31) / 32, (cs + 4 * NEXAR_GEO2_WARPS - 1) / (4 * NEXAR_GEO2_WARPS), n_clips * ((a->frames_per_clip + NEXAR_GEO2_FRAMES - 1) / NEXAR_GEO2_FRAMES));
+#define NEXAR_GEO_SPEC(BHV, BWV, CSV)                                                   \
+  {                                                                                     \
+    if (tail) geometry_spec_kernel<DstT, true, BHV, BWV, CSV><<<sgrid, 32 * NEXAR_GEO2_WARPS, 0, st>>>(P, K); \
+    else geometry_spec_kernel<DstT, false, BHV, BWV, CSV><<<sgrid, 32 * NEXAR_GEO2_WARPS, 0, st>>>(P, K);  \
+  }
+    if (planar && K.bh == 125 && K.bw == 224 && cs == 224) NEXAR_GEO_SPEC(125, 224, 224)
+    else if (planar && K.bh == 180 && K.bw == 320 && cs == 320) NEXAR_GEO_SPEC(180, 320, 320)
+    else {
+      const dim3 ggrid((cs + 31) / 32, (cs + 16 * kGeoPasses - 1) / (16 * kGeoPasses), n_clips * ((a->frames_per_clip + kGeoFrames - 1) / kGeoFrames));
+      if (tail)
+        geometry_kernel<DstT, true><<<ggrid, 256, 0, st>>>(P, K);
+      else
+        geometry_kernel<DstT, false><<<ggrid, 256, 0, st>>>(P, K);
+    }
+#undef NEXAR_GEO_SPEC
     g_launches += 2;
   };
   if (use_fast) {
@@ -2023,6 +2324,35 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   return NEXAR_OK;
 }
 
+// Optional chunking of a batch into groups of whole clips (K1, K2, K3 of a chunk back to back; every chunk has its own
+// slice of the workspace; the result does not depend on it).  Measured on B200 it does NOT pay: at cfg2 (115 MB of
+// intermediate) 3 chunks cost 0.488 ms against 0.429 ms unchunked, at cfg3 (3.8 GB) every chunk size from 3 to 8 clips is
+// slower than one launch set (9.4 ms) — the smaller resize grids lose more to wave quantisation and launch gaps than the
+// L2 hits of the colour / geometry kernels win.  So the default is one chunk; nexar_set_chunk_clips keeps the experiment.
+template <typename SrcT, typename DstT>
+static int launch_chunked(const NexarPlan* p, const NexarTransformArgs* a, const KArgs& K0, int aug_mode, int blur_mode) {
+  const int n = a->n_clips, T = a->frames_per_clip;
+  const int chunk = g_chunk_clips > 0 ? imin(n, g_chunk_clips) : n;
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int nc = imin(chunk, n - c0);
+    const size_t f0 = (size_t)c0 * T;
+    KArgs K = K0;
+    K.frame_offsets = K0.frame_offsets + f0;
+    K.params = K0.params + c0;
+    K.dst = (DstT*)K0.dst + (int64_t)c0 * K0.sb;
+    K.clip_max = K0.clip_max + c0 + f0;            // [nc clip flags | nc * T frame counters], one memset per chunk
+    K.frame_done = K.clip_max + nc;
+    K.gray_partial = K0.gray_partial + 2 * f0 * kMaxBands;
+    K.finfo = K0.finfo + f0;
+    K.inter = K0.inter + f0 * K0.bh * K0.bw;
+    K.canvas = K0.canvas + f0 * 3 * (size_t)p->g.canvas * p->g.canvas;
+    K.n_frames = nc * T;
+    const int rc = launch_all<SrcT, DstT>(p, a, K, nc, aug_mode, blur_mode);
+    if (rc != NEXAR_OK) return rc;
+  }
+  return NEXAR_OK;
+}
+
 extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs* a) {
   g_launches = 0;
   if (!p || !a) return fail(NEXAR_ERR_INVALID, "clip_transform: null argument");
@@ -2076,9 +2406,9 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
     if (span >= 2147483647.0) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: destination strides span more than 2^31 elements per frame");
   }
   if (p->src_dtype == NEXAR_SRC_U8) {
-    if (a->dst_dtype == NEXAR_DST_F32) return launch_all<uint8_t, float>(p, a, K, aug_mode, blur_mode);
-    return launch_all<uint8_t, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
+    if (a->dst_dtype == NEXAR_DST_F32) return launch_chunked<uint8_t, float>(p, a, K, aug_mode, blur_mode);
+    return launch_chunked<uint8_t, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
   }
-  if (a->dst_dtype == NEXAR_DST_F32) return launch_all<float, float>(p, a, K, aug_mode, blur_mode);
-  return launch_all<float, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
+  if (a->dst_dtype == NEXAR_DST_F32) return launch_chunked<float, float>(p, a, K, aug_mode, blur_mode);
+  return launch_chunked<float, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
 }
