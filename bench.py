@@ -459,12 +459,19 @@ def main():
     value = world * b / (ms_step * 1e-3)
 
     # ---- end to end: pinned host clips -> H2D -> transform -> D2H (through the public host API) ----
-    e2e = None
-    if not args.no_e2e:
-        eb = min(b, 32)                            # host batch of the e2e leg (pinned memory: 44-88 MB per clip)
-        pipe = HostClipPipeline(tf, n_clips=eb, frames=t, height=h, width=w, device=dev)
+    def run_e2e(pixel_format):
+        """The same metric through HostClipPipeline with HOST buffers: every step copies its input clips from pinned
+        host memory and reads the result back.  pixel_format "rgb": the uint8 RGB frames the reference's decoder
+        delivers (44 MB per cfg2 clip); "nv12": decoder surfaces (22 MB per clip), converted on the device."""
+        eb = min(b, 32)                            # host batch of the e2e leg (pinned memory: 22-88 MB per clip)
+        pipe = HostClipPipeline(tf, n_clips=eb, frames=t, height=h, width=w, device=dev, pixel_format=pixel_format)
         host_in = pipe.pinned_input()
-        host_in.copy_(clips[:eb].cpu())
+        if pixel_format == "nv12":
+            from vision_collision_detection_b200.synth import rgb_to_nv12
+            for i in range(eb):
+                host_in[i].copy_(rgb_to_nv12(clips[i]).cpu())
+        else:
+            host_in.copy_(clips[:eb].cpu())
         e2e_steps = max(3, min(args.steps, 8))
         host_in2 = pipe.pinned_input()          # two input batches alternate: one is being copied while the next is "decoded"
         host_in2.copy_(host_in)
@@ -495,27 +502,34 @@ def main():
             dist.all_gather(h2d_all, h2d_rank)
         else:
             h2d_all = [h2d_rank]
-        e2e = {"value": world * eb / (float(ems.item()) * 1e-3), "unit": "clips/s",
+        res = {"value": world * eb / (float(ems.item()) * 1e-3), "unit": "clips/s", "source": pixel_format,
                "h2d_bytes_per_step": int(host_in.numel()), "d2h_bytes_per_step": int(host_out.numel() * host_out.element_size()),
                "steps": e2e_steps, "clips_per_gpu_per_step": eb,
                "h2d_GBs_per_gpu": [round(float(x.item()), 2) for x in h2d_all],
-               "h2d_GBs_aggregate": round(sum(float(x.item()) for x in h2d_all), 2),
-               "note": "uint8 source over PCIe (44 MB per cfg2 clip) bounds this leg; see DESIGN.md (F1: NV12 source halves it)"}
+               "h2d_GBs_aggregate": round(sum(float(x.item()) for x in h2d_all), 2)}
         del pipe, host_in, host_in2, ins
+        return res
+
+    e2e = e2e_nv12 = None
+    if not args.no_e2e:
+        e2e = run_e2e("rgb")
+        e2e["note"] = ("uint8 RGB over PCIe (the frames the reference's decoder delivers) bounds this leg; e2e_nv12 is the same "
+                       "call fed with decoder surfaces (half the bytes), DESIGN.md F1")
+        e2e_nv12 = run_e2e("nv12")
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         per_clip = algorithmic_bytes_per_clip(t, h, w, cs, out.element_size())
         step_bytes = b * per_clip
         step_ach = step_bytes / (ms_step * 1e-3) / 1e9
-        # dominant kernel: resize_fast_kernel.  With augmentation it is the fused cluster kernel (resize + colour + affine +
-        # normalise + store = the whole transform of the batch); without, the resize + normalise + store kernel.  Either way
-        # its algorithmic bytes are the step's: source read once + output written once.
+        # dominant kernel: resize_fast_kernel (the only one that touches the source).  The sub-record divides the STEP's
+        # algorithmic bytes (source read once + output written once) by that kernel's own duration, i.e. what the step
+        # would reach if the colour / geometry kernels were free; the headline fraction below is the whole step.
         k_ms = (sum(k1_ms) / args.steps) if k1_ms else None   # per step: the sum over the chunks of a step
         kern = None
         if k_ms:
             k_ach = step_bytes / (k_ms * 1e-3) / 1e9
-            kern = {"name": "resize_fast_kernel" + (" (fused: resize+colour+affine+normalise)" if args.mode == "custom" else ""),
+            kern = {"name": "resize_fast_kernel" + (" (then colour_kernel + geometry_spec_kernel)" if args.mode == "custom" else ""),
                     "ms": k_ms, "achieved": k_ach, "frac": k_ach / peaks["hbm_gbs"], "share_of_step": k_ms / ms_step,
                     "timed": "CUDA event pair around the launch on its stream, every timed step (nexar_profile_begin/end)"}
         # roofline.frac is STEP level (all launches of the step, device events): it is never better than the kernel's own
@@ -540,7 +554,7 @@ def main():
                        "sharding": f"{b} clips per GPU, no collective" + (" (one 256-clip batch split over the GPUs)" if scaling == "strong" else ""),
                        "preheat": "60 ms of torch copies before the warm-up (clock ramp; not transform steps)"},
             "output_GBs": world * b * 3 * t * cs * cs * out.element_size() / (ms_step * 1e-3) / 1e9,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_nv12": e2e_nv12, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -45,7 +45,13 @@ enum {
   NEXAR_ERR_UNSUPPORTED = -4
 };
 
-enum { NEXAR_SRC_U8 = 0, NEXAR_SRC_F32 = 1 };              /* source frames: packed RGB, HWC */
+/* Source frames.  U8 / F32: packed RGB, HWC.  NV12: what a hardware decoder emits (replaces the CPU decode + RGB
+ * conversion of decord.VideoReader / cv2, nexar_videos.py:360,422): a Y plane [H][src_row_stride] followed by the
+ * interleaved chroma plane [H/2][src_row_stride] (U0 V0 U1 V1 ...), 1.5 bytes per pixel; converted on the device to
+ * RGB bytes with the BT.601 limited-range integer formula (C = Y-16, D = U-128, E = V-128; R = clip((298C+409E+128)>>8),
+ * G = clip((298C-100D-208E+128)>>8), B = clip((298C+516D+128)>>8); nearest-neighbour chroma), then identical to U8.
+ * frame_offsets then point at the Y planes; the workspace grows by one RGB copy of the batch. */
+enum { NEXAR_SRC_U8 = 0, NEXAR_SRC_F32 = 1, NEXAR_SRC_NV12 = 2 };
 enum { NEXAR_DST_F32 = 0, NEXAR_DST_BF16 = 1 };
 
 /* NexarClipParams.flags */

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 NEXAR_ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-SRC_U8, SRC_F32 = 0, 1
+SRC_U8, SRC_F32, SRC_NV12 = 0, 1, 2
 DST_F32, DST_BF16 = 0, 1
 FLIP, AUG, AFFINE, GRAYSCALE, NOISE, BLUR, POSTERIZE, SOLARIZE, INVERT, CUTOUT = (1 << i for i in range(10))
 MAX_CUTOUT = 8

@@ -92,7 +92,7 @@ struct NexarPlan {
 static const int kMaxPairs = 1024;
 static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_al) {
   const NexarGeometry& g = p->g;
-  if (p->src_dtype != NEXAR_SRC_U8) return false;
+  if (p->src_dtype != NEXAR_SRC_U8 && p->src_dtype != NEXAR_SRC_NV12) return false;
   if ((g.src_w * 3) % 16 != 0 || g.src_w * 3 / 16 > 384 || (g.src_h & 1)) return false;  // rows are consumed in pairs
   if (g.src_h < 2 * g.resize_h || g.src_w < g.resize_w) return false;  // vertical down-scale by >= 2
   if (imin_host(g.resize_w, g.canvas) > 384) return false;
@@ -327,7 +327,10 @@ extern "C" int nexar_aa_taps(int32_t in_size, int32_t out_size, int32_t* start, 
 
 extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, NexarPlan** out) {
   if (!g || !out) return fail(NEXAR_ERR_INVALID, "plan_create: null argument");
-  if (src_dtype != NEXAR_SRC_U8 && src_dtype != NEXAR_SRC_F32) return fail(NEXAR_ERR_INVALID, "plan_create: bad src_dtype");
+  if (src_dtype != NEXAR_SRC_U8 && src_dtype != NEXAR_SRC_F32 && src_dtype != NEXAR_SRC_NV12)
+    return fail(NEXAR_ERR_INVALID, "plan_create: bad src_dtype");
+  if (src_dtype == NEXAR_SRC_NV12 && ((g->src_h | g->src_w) & 1))
+    return fail(NEXAR_ERR_INVALID, "plan_create: NV12 frames need an even height and width");
   if (g->src_h <= 0 || g->src_w <= 0 || g->canvas <= 0 || g->resize_h <= 0 || g->resize_w <= 0)
     return fail(NEXAR_ERR_INVALID, "plan_create: bad geometry");
   NexarPlan* p = new NexarPlan();
@@ -437,6 +440,8 @@ struct Workspace {
   FrameInfo* finfo;     // [n_frames] per-frame constants for K2/K3, written by K1.5
   uint2* inter;         // [n_frames][bh][bw]   q15 RGBX pixels (8 bytes), brightness-adjusted, then colour-adjusted in place
   float* canvas;        // [n_frames][3][cs][cs] pre-blur canvas (blur path only)
+  int64_t* rgb_offsets; // [n_frames] NV12 sources: byte offsets of the converted frames in `rgb`
+  unsigned char* rgb;   // [n_frames][src_h][src_w][3] NV12 sources: packed RGB produced by nv12_to_rgb_kernel
   size_t total;
 };
 
@@ -457,6 +462,13 @@ static Workspace carve(const NexarPlan* p, int n_clips, int T, void* base, unsig
   if (any_flags & NEXAR_AUG) off = align_up(off + nf * bh * bw * sizeof(uint2), 256);
   w.canvas = (float*)(b + off);  // only the blur path uses it
   if (any_flags & NEXAR_BLUR) off = align_up(off + nf * 3 * (size_t)p->g.canvas * p->g.canvas * sizeof(float), 256);
+  w.rgb_offsets = (int64_t*)(b + off);
+  w.rgb = nullptr;
+  if (p->src_dtype == NEXAR_SRC_NV12) {
+    off = align_up(off + nf * sizeof(int64_t), 256);
+    w.rgb = (unsigned char*)(b + off);
+    off = align_up(off + nf * (size_t)p->g.src_h * p->g.src_w * 3, 256);
+  }
   w.total = off;
   return w;
 }
@@ -2141,6 +2153,97 @@ __global__ void __launch_bounds__(256) blur_kernel(DevPlan P, KArgs A) {
 }
 
 // ---------------------------------------------------------------------------------
+// NV12 sources (what a hardware decoder produces: 1.5 bytes per pixel instead of 3).  Y plane [H][pitch], then the
+// interleaved chroma plane [H/2][pitch] (U0 V0 U1 V1 ...), one chroma pair per 2 x 2 pixels (nearest neighbour).
+// Conversion = ITU-R BT.601 limited range in its classic 8-bit integer form,
+//   C = Y - 16, D = U - 128, E = V - 128
+//   R = clip((298 C + 409 E + 128) >> 8)   G = clip((298 C - 100 D - 208 E + 128) >> 8)   B = clip((298 C + 516 D + 128) >> 8)
+// to packed RGB bytes — exactly the uint8 frames the resize kernels take, so everything downstream (the /255 rule on the
+// clip maximum included) is the RGB path bit for bit (oracle/nv12_oracle.py states the same formula in numpy).
+// clip(x >> 8) is evaluated as clamp(x, 0, 65535) >> 8, so the shift merges with the byte packing.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int clamp_u16(int x) { return min(max(x, 0), 65535); }
+struct ChromaTerms { int r, g, b; };
+__device__ __forceinline__ ChromaTerms chroma_terms(int u, int v) {
+  const int d = u - 128, e = v - 128;
+  constexpr int base = -298 * 16 + 128;
+  return {409 * e + base, -100 * d - 208 * e + base, 516 * d + base};
+}
+
+// 16 pixels of two rows per thread: three 16-byte loads, six 16-byte stores
+__global__ void __launch_bounds__(256) nv12_to_rgb_vec_kernel(const unsigned char* __restrict__ src, const int64_t* __restrict__ frame_offsets,
+                                                              int64_t pitch, int H, int W, unsigned char* __restrict__ rgb,
+                                                              int64_t* __restrict__ out_offsets) {
+  const int frame = blockIdx.y;
+  const int cols = W >> 4;
+  const int unit = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t fbytes = (int64_t)H * W * 3;
+  if (unit == 0) out_offsets[frame] = (int64_t)frame * fbytes;
+  if (unit >= cols * (H >> 1)) return;
+  const int r2 = unit / cols, c = unit - r2 * cols;
+  const unsigned char* f = src + frame_offsets[frame];
+  const uint4 ya = __ldcs((const uint4*)(f + (int64_t)(2 * r2) * pitch + 16 * c));
+  const uint4 yb = __ldcs((const uint4*)(f + (int64_t)(2 * r2 + 1) * pitch + 16 * c));
+  const uint4 uv = __ldcs((const uint4*)(f + (int64_t)(H + r2) * pitch + 16 * c));
+  const unsigned yaw[4] = {ya.x, ya.y, ya.z, ya.w}, ybw[4] = {yb.x, yb.y, yb.z, yb.w}, uvw[4] = {uv.x, uv.y, uv.z, uv.w};
+  unsigned oa[12], ob[12];   // 48 output bytes per row
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // four pixels (two chroma pairs) per 32-bit word of luma
+    const ChromaTerms t0 = chroma_terms(uvw[q] & 255u, (uvw[q] >> 8) & 255u);
+    const ChromaTerms t1 = chroma_terms((uvw[q] >> 16) & 255u, uvw[q] >> 24);
+    unsigned char* pa = (unsigned char*)oa + 12 * q;
+    unsigned char* pb = (unsigned char*)ob + 12 * q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const ChromaTerms& t = k < 2 ? t0 : t1;
+      const int la = 298 * (int)((yaw[q] >> (8 * k)) & 255u), lb = 298 * (int)((ybw[q] >> (8 * k)) & 255u);
+      pa[3 * k + 0] = (unsigned char)(clamp_u16(la + t.r) >> 8);
+      pa[3 * k + 1] = (unsigned char)(clamp_u16(la + t.g) >> 8);
+      pa[3 * k + 2] = (unsigned char)(clamp_u16(la + t.b) >> 8);
+      pb[3 * k + 0] = (unsigned char)(clamp_u16(lb + t.r) >> 8);
+      pb[3 * k + 1] = (unsigned char)(clamp_u16(lb + t.g) >> 8);
+      pb[3 * k + 2] = (unsigned char)(clamp_u16(lb + t.b) >> 8);
+    }
+  }
+  unsigned char* o = rgb + (int64_t)frame * fbytes + ((int64_t)(2 * r2) * W + 16 * c) * 3;
+  uint4* da = (uint4*)o;
+  uint4* db = (uint4*)(o + (int64_t)W * 3);
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    da[v] = make_uint4(oa[4 * v], oa[4 * v + 1], oa[4 * v + 2], oa[4 * v + 3]);
+    db[v] = make_uint4(ob[4 * v], ob[4 * v + 1], ob[4 * v + 2], ob[4 * v + 3]);
+  }
+}
+
+// any even size / pitch / alignment: one 2 x 2 block per thread
+__global__ void __launch_bounds__(256) nv12_to_rgb_any_kernel(const unsigned char* __restrict__ src, const int64_t* __restrict__ frame_offsets,
+                                                              int64_t pitch, int H, int W, unsigned char* __restrict__ rgb,
+                                                              int64_t* __restrict__ out_offsets) {
+  const int frame = blockIdx.y;
+  const int cols = W >> 1;
+  const int unit = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t fbytes = (int64_t)H * W * 3;
+  if (unit == 0) out_offsets[frame] = (int64_t)frame * fbytes;
+  if (unit >= cols * (H >> 1)) return;
+  const int r2 = unit / cols, c = unit - r2 * cols;
+  const unsigned char* f = src + frame_offsets[frame];
+  const unsigned char* uvp = f + (int64_t)(H + r2) * pitch + 2 * c;
+  const ChromaTerms t = chroma_terms(uvp[0], uvp[1]);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const unsigned char* yp = f + (int64_t)(2 * r2 + dy) * pitch + 2 * c;
+    unsigned char* o = rgb + (int64_t)frame * fbytes + ((int64_t)(2 * r2 + dy) * W + 2 * c) * 3;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int l = 298 * (int)yp[dx];
+      o[3 * dx + 0] = (unsigned char)(clamp_u16(l + t.r) >> 8);
+      o[3 * dx + 1] = (unsigned char)(clamp_u16(l + t.g) >> 8);
+      o[3 * dx + 2] = (unsigned char)(clamp_u16(l + t.b) >> 8);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------------
 static int sm_count() {  // of the current device (cached per device)
@@ -2190,7 +2293,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   const int vis_rows = imin(p->g.resize_h, p->g.canvas);
   const bool prof = (size_t)(2 * g_prof_n + 1) < g_prof_ev.size();
   const bool use_fast = std::is_same<SrcT, uint8_t>::value && p->fast_ok && covers_source && g_resize_variant != 1 &&
-                        a->src_row_stride % 16 == 0 && ((uintptr_t)a->src % 16) == 0;
+                        K.src_row_stride % 16 == 0 && ((uintptr_t)K.src % 16) == 0;
   bool tail_done = false;  // K2 / K3's work has already been enqueued
   int nbands = 1;
   auto launch_tail = [&]() {  // K1.5 + K2 + K3 (K.pass == 4: only the clips whose maximum was > 1)
@@ -2262,7 +2365,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
 #define NEXAR_FAST(KXV, NTV, MB) NEXAR_FAST_RS(KXV, NTV, MB, 0)
 // tightly packed 720p / 1080p rows get the row stride as a compile-time constant (immediate load offsets)
 #define NEXAR_FAST_SPEC(KXV, NTV, MB, RSV) \
-  if (a->src_row_stride == RSV) NEXAR_FAST_RS(KXV, NTV, MB, RSV) else NEXAR_FAST_RS(KXV, NTV, MB, 0)
+  if (K.src_row_stride == RSV) NEXAR_FAST_RS(KXV, NTV, MB, RSV) else NEXAR_FAST_RS(KXV, NTV, MB, 0)
     if (need_threads <= 256) {
       if (kx == 10) NEXAR_FAST(10, 256, NEXAR_MINB) else if (kx == 14) NEXAR_FAST_SPEC(14, 256, NEXAR_MINB, 3840) else NEXAR_FAST(20, 256, 2)
     } else if (need_threads <= 320) {
@@ -2366,14 +2469,33 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   if (!a->workspace || a->workspace_bytes < need) return fail(NEXAR_ERR_WORKSPACE, "clip_transform: workspace too small");
   for (int c = 0; c < 3; ++c)
     if (a->normalize && !(a->std[c] != 0.0f)) return fail(NEXAR_ERR_INVALID, "clip_transform: std must be non-zero");
-  const size_t esz = p->src_dtype == NEXAR_SRC_U8 ? 1 : 4;
-  if (a->src_row_stride < (int64_t)(p->g.src_w * 3 * esz)) return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
+  const bool nv12 = p->src_dtype == NEXAR_SRC_NV12;
+  const size_t esz = p->src_dtype == NEXAR_SRC_F32 ? 4 : 1;
+  if (a->src_row_stride < (int64_t)(nv12 ? p->g.src_w : p->g.src_w * 3 * esz))
+    return fail(NEXAR_ERR_INVALID, "clip_transform: src_row_stride smaller than a row");
 
   Workspace w = carve(p, a->n_clips, a->frames_per_clip, a->workspace, a->any_flags);
   KArgs K;
   K.src = a->src;
   K.frame_offsets = a->frame_offsets;
   K.src_row_stride = a->src_row_stride;
+  if (nv12) {
+    // decoder surfaces -> packed RGB bytes in the workspace (one launch), then the uint8 path on those
+    const int H = p->g.src_h, W = p->g.src_w, nf = a->n_clips * a->frames_per_clip;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const bool vec = (W % 16) == 0 && (a->src_row_stride % 16) == 0 && (((uintptr_t)a->src) & 15) == 0;
+    if (vec)
+      nv12_to_rgb_vec_kernel<<<dim3(((W / 16) * (H / 2) + 255) / 256, nf), 256, 0, st>>>(
+          (const unsigned char*)a->src, a->frame_offsets, a->src_row_stride, H, W, w.rgb, w.rgb_offsets);
+    else
+      nv12_to_rgb_any_kernel<<<dim3(((W / 2) * (H / 2) + 255) / 256, nf), 256, 0, st>>>(
+          (const unsigned char*)a->src, a->frame_offsets, a->src_row_stride, H, W, w.rgb, w.rgb_offsets);
+    CUDA_TRY(cudaGetLastError());
+    ++g_launches;
+    K.src = w.rgb;
+    K.frame_offsets = w.rgb_offsets;
+    K.src_row_stride = (int64_t)W * 3;
+  }
   K.params = a->params;
   K.dst = a->dst;
   K.sb = a->dst_stride[0];
@@ -2405,7 +2527,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
     const double span = 2.0 * std::fabs((double)K.sc) + (double)(p->g.canvas - 1) * (std::fabs((double)K.sy) + std::fabs((double)K.sx));
     if (span >= 2147483647.0) return fail(NEXAR_ERR_UNSUPPORTED, "clip_transform: destination strides span more than 2^31 elements per frame");
   }
-  if (p->src_dtype == NEXAR_SRC_U8) {
+  if (p->src_dtype != NEXAR_SRC_F32) {
     if (a->dst_dtype == NEXAR_DST_F32) return launch_chunked<uint8_t, float>(p, a, K, aug_mode, blur_mode);
     return launch_chunked<uint8_t, __nv_bfloat16>(p, a, K, aug_mode, blur_mode);
   }

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 _DST = {torch.float32: _lib.DST_F32, torch.bfloat16: _lib.DST_BF16}
-_SRC = {torch.uint8: _lib.SRC_U8, torch.float32: _lib.SRC_F32}
+_SRC = {torch.uint8: _lib.SRC_U8, torch.float32: _lib.SRC_F32, "nv12": _lib.SRC_NV12}
 
 # output layouts: name -> (shape builder, element strides for (clip, channel, frame, y, x))
 LAYOUTS = ("BCTHW", "BTCHW", "BTHWC")
@@ -83,6 +83,7 @@ class ClipTransformEngine:
         return p
 
     def letterbox_plan(self, h: int, w: int, cs: int, src_dtype=torch.uint8) -> Plan:
+        """``src_dtype``: torch.uint8 / torch.float32 (packed RGB) or the string "nv12" (decoder surfaces)."""
         return self.plan(_lib.letterbox_geometry(h, w, cs), _SRC[src_dtype])
 
     def resize_crop_plan(self, h: int, w: int, size: int, cs: int, src_dtype=torch.uint8) -> Plan:
@@ -134,13 +135,14 @@ class ClipTransformEngine:
         if out.dtype not in _DST:
             raise TypeError(f"unsupported output dtype {out.dtype}")
         g = plan.geom
-        esz = 1 if plan.src_dtype == _lib.SRC_U8 else 4
+        esz = 4 if plan.src_dtype == _lib.SRC_F32 else 1
+        row = g.src_w if plan.src_dtype == _lib.SRC_NV12 else g.src_w * 3 * esz   # NV12: the pitch of the Y / UV planes
         a = _lib.TransformArgs()
         a.struct_size = C.sizeof(_lib.TransformArgs)
         a.n_clips, a.frames_per_clip = n_clips, frames_per_clip
         a.src = src.data_ptr()
         a.frame_offsets = frame_offsets.data_ptr()
-        a.src_row_stride = src_row_stride if src_row_stride is not None else g.src_w * 3 * esz
+        a.src_row_stride = src_row_stride if src_row_stride is not None else row
         a.params = params_dev.data_ptr()
         a.any_flags = any_flags
         a.dst = out.data_ptr()

@@ -17,16 +17,22 @@ from .video_aug import GpuVideoTransform
 
 class HostClipPipeline:
     def __init__(self, transform: GpuVideoTransform, n_clips: int, frames: int, height: int, width: int,
-                 device=None, clips_per_chunk: int = 4, n_streams: int = 3, out_dtype: Optional[torch.dtype] = None):
+                 device=None, clips_per_chunk: int = 4, n_streams: int = 3, out_dtype: Optional[torch.dtype] = None,
+                 pixel_format: str = "rgb"):
+        """``pixel_format="nv12"``: the host clips are decoder surfaces, uint8 ``[B,T,H*3/2,W]`` — half the bytes of
+        RGB over PCIe (the link is what bounds this path), converted to RGB on the device."""
         self.tf = transform
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.shape = (n_clips, frames, height, width, 3)
+        if pixel_format not in ("rgb", "nv12"):
+            raise ValueError(f"unknown pixel_format {pixel_format!r}")
+        self.pixel_format = pixel_format
+        self.shape = (n_clips, frames, height * 3 // 2, width) if pixel_format == "nv12" else (n_clips, frames, height, width, 3)
         self.chunk = max(1, min(clips_per_chunk, n_clips))
         self.out_dtype = out_dtype or transform.out_dtype
         cs = transform.crop_size
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
         self.engines = [ClipTransformEngine(self.device) for _ in range(n_streams)]
-        self.dev_in = [torch.empty((self.chunk, frames, height, width, 3), dtype=torch.uint8, device=self.device)
+        self.dev_in = [torch.empty((self.chunk,) + self.shape[1:], dtype=torch.uint8, device=self.device)
                        for _ in range(n_streams)]
         self.dev_out = [torch.empty((self.chunk, 3, frames, cs, cs), dtype=self.out_dtype, device=self.device)
                         for _ in range(n_streams)]
@@ -47,7 +53,8 @@ class HostClipPipeline:
             raise ValueError(f"expected uint8 {self.shape}")
         n = self.shape[0]
         if params is None:
-            params = self.tf.sample_params(n, self.shape[2], self.shape[3])
+            h = self.shape[2] * 2 // 3 if self.pixel_format == "nv12" else self.shape[2]
+            params = self.tf.sample_params(n, h, self.shape[3])
         slot = self._slot
         self._slot ^= 1
         host_out = self.host_outs[slot]
@@ -60,7 +67,8 @@ class HostClipPipeline:
                 din = self.dev_in[i][: hi - lo]
                 din.copy_(host_clips[lo:hi], non_blocking=True)
                 dout = self.dev_out[i][: hi - lo]
-                self.tf.forward_batch(din, params=params[lo:hi], out=dout, engine=self.engines[i])
+                self.tf.forward_batch(din, params=params[lo:hi], out=dout, engine=self.engines[i],
+                                      pixel_format=self.pixel_format)
                 host_out[lo:hi].copy_(dout, non_blocking=True)
         for i, s in enumerate(self.streams):
             self._done[slot][i].record(s)
@@ -74,5 +82,5 @@ class HostClipPipeline:
 
     @torch.no_grad()
     def run(self, host_clips: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None) -> torch.Tensor:
-        """host_clips: pinned uint8 [B,T,H,W,3].  Returns the pinned [B,3,T,cs,cs] result (valid on return)."""
+        """host_clips: pinned uint8 [B,T,H,W,3] (or [B,T,H*3/2,W] for nv12).  Returns the pinned [B,3,T,cs,cs] result (valid on return)."""
         return self.wait(self.submit(host_clips, params))

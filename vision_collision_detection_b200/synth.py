@@ -57,3 +57,31 @@ def make_clip_torch(t: int, h: int, w: int, seed: int = 0, kind: str = "noise", 
     cc = ar(3).view(1, 1, 1, 3)
     lin = ((tt * h + yy) * w + xx) * 3 + cc
     return _pattern(tt, yy, xx, cc, h, seed, kind, lin).to(torch.uint8)
+
+
+def rgb_to_nv12(clip):
+    """Synthetic decoder surfaces from RGB frames: uint8 ``[...,H,W,3]`` -> uint8 ``[...,H*3/2,W]`` (Y plane, then the
+    interleaved UV plane of the 2 x 2 block means), BT.601 limited range in the usual 8-bit integer form
+    (Y = ((66R + 129G + 25B + 128) >> 8) + 16, U = ((-38R - 74G + 112B + 128) >> 8) + 128, V = ((112R - 94G - 18B + 128) >> 8) + 128).
+    Works on numpy arrays and torch tensors (integer arithmetic only, identical bytes)."""
+    is_np = isinstance(clip, np.ndarray)
+    x = clip.astype(np.int32) if is_np else clip.int()
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    y = ((66 * r + 129 * g + 25 * b + 128) >> 8) + 16
+    h, w = y.shape[-2], y.shape[-1]
+    if h % 2 or w % 2:
+        raise ValueError("nv12 needs an even height and width")
+
+    def blocks(v):  # mean of each 2 x 2 block, rounded
+        v = v.reshape(v.shape[:-2] + (h // 2, 2, w // 2, 2))
+        return (v.sum(axis=-1).sum(axis=-2) + 2) >> 2 if is_np else (v.sum(dim=-1).sum(dim=-2) + 2) >> 2
+
+    rm, gm, bm = blocks(r), blocks(g), blocks(b)
+    u = ((-38 * rm - 74 * gm + 112 * bm + 128) >> 8) + 128
+    v = ((112 * rm - 94 * gm - 18 * bm + 128) >> 8) + 128
+    if is_np:
+        uv = np.stack([u, v], axis=-1).reshape(u.shape[:-1] + (w,))
+        return np.concatenate([y, uv], axis=-2).clip(0, 255).astype(np.uint8)
+    import torch
+    uv = torch.stack([u, v], dim=-1).reshape(u.shape[:-1] + (w,))
+    return torch.cat([y, uv], dim=-2).clamp(0, 255).to(torch.uint8)

@@ -145,11 +145,22 @@ class GpuVideoTransform(nn.Module):
     def forward_batch(self, frames: torch.Tensor, params: Optional[List[Dict[str, Any]]] = None,
                       frame_index: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                       layout: str = "BCTHW", out_dtype: Optional[torch.dtype] = None, rng=random,
-                      engine=None) -> torch.Tensor:
+                      engine=None, pixel_format: str = "rgb") -> torch.Tensor:
         """frames: CUDA ``[B,T,H,W,3]`` (uint8 or float32, contiguous) — or, with ``frame_index``
         (int64 ``[B,T']`` indices into the flattened ``B*T`` frame axis), a frame pool from which each
-        output clip gathers its frames (temporal sampling without a copy).  Returns ``[B,3,T',cs,cs]``."""
-        if frames.dim() != 5 or frames.shape[-1] != 3:
+        output clip gathers its frames (temporal sampling without a copy).  Returns ``[B,3,T',cs,cs]``.
+
+        ``pixel_format="nv12"``: frames are decoder surfaces, uint8 ``[B,T,H*3/2,W]`` (Y plane, then the
+        interleaved UV plane), 1.5 bytes per pixel; they are converted on the device (BT.601 limited range,
+        include/nexar_clip_transform.h) to the RGB bytes the reference's decoder would have delivered
+        (nexar_videos.py:360,422) and take the uint8 path from there."""
+        nv12 = pixel_format == "nv12"
+        if pixel_format not in ("rgb", "nv12"):
+            raise ValueError(f"unknown pixel_format {pixel_format!r}")
+        if nv12:
+            if frames.dim() != 4 or frames.dtype != torch.uint8 or frames.shape[2] % 3 or frames.shape[3] % 2:
+                raise ValueError(f"nv12 frames are uint8 [B,T,H*3/2,W] with even H and W, got {frames.dtype} {tuple(frames.shape)}")
+        elif frames.dim() != 5 or frames.shape[-1] != 3:
             raise ValueError(f"expected [B,T,H,W,3], got {tuple(frames.shape)}")
         if not frames.is_cuda:
             raise ValueError("forward_batch needs device-resident frames (use forward() for host tensors)")
@@ -158,8 +169,12 @@ class GpuVideoTransform(nn.Module):
         if not frames.is_contiguous():
             frames = frames.contiguous()
         eng = engine if engine is not None else get_engine(frames.device)
-        b, t, h, w, _ = frames.shape
-        frame_bytes = h * w * 3 * frames.element_size()
+        if nv12:
+            b, t, h, w = frames.shape[0], frames.shape[1], frames.shape[2] * 2 // 3, frames.shape[3]
+            frame_bytes = h * w * 3 // 2
+        else:
+            b, t, h, w, _ = frames.shape
+            frame_bytes = h * w * 3 * frames.element_size()
         if frame_index is not None:
             if frame_index.dim() != 2:
                 raise ValueError("frame_index must be [n_clips, frames_per_clip]")
@@ -183,7 +198,9 @@ class GpuVideoTransform(nn.Module):
         self.last_params = params
         packed, any_flags = pack_clip_params(params, self.crop_size, self.video_aug)
         two_pass = self.resize_short_side is not None and self.use_letterbox
-        plan = None if two_pass else self._plan(eng, h, w, frames.dtype)
+        if nv12 and two_pass:
+            raise ValueError("nv12 frames are not supported by the two-pass (short-side resize + letterbox) variant")
+        plan = None if two_pass else self._plan(eng, h, w, "nv12" if nv12 else frames.dtype)
         dt = out_dtype or self.out_dtype
         if out is None:
             out, strides = _alloc_out(layout, n_clips, t_out, self.crop_size, dt, frames.device)
