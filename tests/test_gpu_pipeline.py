@@ -221,3 +221,50 @@ def test_loader_with_forked_workers_and_mixed_resolutions():
                 assert float(np.abs(got - want).max()) <= TOL_AFTER
                 checked += 1
     assert checked == 5 and torch.all(out[0][2] == 0)          # the broken video is the all-zeros clip
+
+
+def test_cfg4_windows_of_a_720p_video_against_the_oracle():
+    """BASELINE configs[3] at the real frame size (the fixed-point fast kernel, not the general one): a 720p video,
+    16-frame windows at stride 8, val chain; windows 0 and the last one against the numpy oracle on the same frames."""
+    from vision_collision_detection_b200.inference import SlidingWindowTransform, sliding_window_starts
+    from vision_collision_detection_b200.synth import make_clip_torch
+    video = make_clip_torch(44, 720, 1280, 17, "dashcam")
+    sw = SlidingWindowTransform(window=16, stride=8, out_dtype=torch.float32)
+    view = sw.windows(video)
+    starts = sliding_window_starts(44, 16, 8)
+    assert starts == [0, 8, 16, 24] and tuple(view.shape) == (4, 3, 16, 224, 224)
+    for k in (0, 3):
+        frames = video[starts[k]:starts[k] + 16:5].cpu().numpy()       # frames 0, 5, 10, 15 of the window
+        want = O.apply_clip_transform(frames.transpose(3, 0, 1, 2), O.TransformConfig(mode="val"), {"flip": False, "aug": None})
+        got = view[k][:, ::5].cpu().numpy()
+        assert np.abs(got - want).max() <= TOL_AFTER
+    bf = SlidingWindowTransform(window=16, stride=8).windows(video, materialize=True)     # bf16, materialised
+    assert bf.is_contiguous() and bf.dtype == torch.bfloat16
+    assert (bf.float() - view).abs().max().item() <= 2.0 ** -6           # one bf16 ulp at |v| < 4
+
+
+def test_window_predictor_is_predict_shaped():
+    """nexar_inference.py:211-331 per window: softmax / argmax, class names, probabilities dict, plus the window position."""
+    from vision_collision_detection_b200.inference import CLASS_MAP, SlidingWindowTransform, WindowPredictor, classify_outputs
+    from vision_collision_detection_b200.synth import make_clip_torch
+    video = make_clip_torch(70, 96, 160, 23, "dashcam")
+    w_mat = torch.tensor([[1.0, -2.0, 0.5], [-0.3, 0.8, 1.1], [0.2, 0.1, -0.9]], device="cuda")
+
+    def model(x):                                   # [b,3,T,cs,cs] -> logits [b,3]: a fixed linear read-out of channel means
+        assert x.is_contiguous() and x.dim() == 5 and x.shape[1] == 3 and x.shape[2] == 16
+        return x.float().mean(dim=(2, 3, 4)) @ w_mat
+
+    wp = WindowPredictor(model, window=16, stride=8, batch_size=3)
+    res = wp.predict(video, video_path="synthetic.mp4", fps=30.0)
+    assert len(res) == 7 and [r["window_start"] for r in res] == [0, 8, 16, 24, 32, 40, 48]
+    view = SlidingWindowTransform(window=16, stride=8, out_dtype=torch.float32).windows(video)
+    logits = view.mean(dim=(2, 3, 4)) @ w_mat
+    probs = torch.softmax(logits, dim=1).cpu().numpy()
+    for k, r in enumerate(res):
+        assert set(r) >= {"predicted_class", "predicted_class_name", "probabilities", "video_path", "window_start", "center_frame"}
+        assert r["predicted_class"] == int(probs[k].argmax()) and r["predicted_class_name"] == CLASS_MAP[r["predicted_class"]]
+        assert list(r["probabilities"]) == ["Normal", "Near Collision", "Collision"]
+        assert np.allclose(list(r["probabilities"].values()), probs[k], atol=1e-5)
+        assert r["center_frame"] == r["window_start"] + 8 and r["video_path"] == "synthetic.mp4"
+    p2, c2 = classify_outputs(torch.tensor([[-2.0], [3.0]]), num_classes=2)            # binary head (:251-259)
+    assert p2.shape == (2, 1) and c2.tolist() == [0, 1]

@@ -300,3 +300,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_reference_import_shims():
+    """nexar_inference.py:203-204 imports ``nexar_data.NvidiaDashcamDataset`` (a module the reference does not ship)
+    and ``nexar_video_aug.create_video_transforms``; the shims make both resolve to the GPU path, only on request."""
+    import importlib
+    import sys
+
+    from vision_collision_detection_b200 import create_video_transforms, shims
+    from vision_collision_detection_b200.videos import GpuDashcamDataset
+    saved = {k: sys.modules.get(k) for k in ("nexar_data", "nexar_video_aug")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        mods = shims.install()
+        assert set(mods) == {"nexar_data"} and "nexar_video_aug" not in sys.modules
+        assert importlib.import_module("nexar_data").NvidiaDashcamDataset is GpuDashcamDataset
+        shims.install(replace_video_aug=True)
+        from nexar_data import NvidiaDashcamDataset          # the reference's own import lines
+        from nexar_video_aug import create_video_transforms as ctf
+        assert NvidiaDashcamDataset is GpuDashcamDataset and ctf is create_video_transforms
+        ds = NvidiaDashcamDataset(metadata_df=[{"id": "video_0", "video_type": "Normal"}], base_dirs=["/nonexistent"], fps=10,
+                                  duration=5, is_train=False, skip_missing=False, transform=None, sample_strategy="center")
+        assert len(ds) == 1                                   # the constructor call of nexar_inference.py:212-221
+        shims.uninstall()
+        assert "nexar_data" not in sys.modules and "nexar_video_aug" not in sys.modules
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)

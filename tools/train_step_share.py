@@ -93,6 +93,9 @@ def main():
         a, s = (t / args.steps).tolist()
         print(json.dumps({"config": "cfg5: convnext_tiny+GRU (random init), fp16 autocast, AdamW, DDP" if world > 1 else
                           "cfg5 (1 GPU): convnext_tiny+GRU (random init), fp16 autocast, AdamW",
+                          "model": "stand-in with the input contract and layer types of nexar_arch.EnhancedFrameCNN('convnext_tiny', "
+                                   "temporal_mode='gru') (nexar_arch.py:390-443), built from torchvision; NOT the reference class",
+                          "aug": "nexar_videos.py:2003-2010 kwargs, device-resident uint8 720p clips -> fp32 [B,3,T,224,224]",
                           "n_gpus": world, "batch_per_gpu": args.batch, "frames": args.frames,
                           "ms_aug": a, "ms_step": s, "aug_share": a / s, "clips_per_s": world * args.batch / (s * 1e-3)}))
     if world > 1:

@@ -15,6 +15,35 @@ from .engine import ClipTransformEngine
 from .video_aug import GpuVideoTransform
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU, so that pinned buffers allocated afterwards
+    (first touch) and the copy-submitting thread sit on the GPU's own NUMA node.  With several ranks per host this is
+    what keeps every GPU's H2D stream off the inter-socket link.  Returns the CPU list, or None when NVML or the
+    affinity call is unavailable (nothing is changed then)."""
+    try:
+        import os
+
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - an optimisation only
+        return None
+
+
 class HostClipPipeline:
     def __init__(self, transform: GpuVideoTransform, n_clips: int, frames: int, height: int, width: int,
                  device=None, clips_per_chunk: int = 4, n_streams: int = 3, out_dtype: Optional[torch.dtype] = None,

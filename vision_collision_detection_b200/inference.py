@@ -12,8 +12,9 @@ shorter than the window is padded by repeating its last frame (nexar_videos.py:4
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Any, Callable, Dict, List, Optional
 
+import numpy as np
 import torch
 
 from .video_aug import GpuVideoTransform, create_video_transforms
@@ -64,3 +65,62 @@ class SlidingWindowTransform:
         view = fr.as_strided((k, 3, self.window, fr.shape[2], fr.shape[3]),
                              (self.stride * s[0], s[1], s[0], s[2], s[3]))
         return view.contiguous() if materialize else view
+
+
+CLASS_MAP = {0: "Normal", 1: "Near Collision", 2: "Collision"}      # nexar_inference.py:239
+
+
+def classify_outputs(outputs: torch.Tensor, num_classes: int = 3):
+    """Logits -> (probabilities [K,C] numpy, predicted classes [K] numpy), the post-processing of
+    nexar_inference.py:250-266 (sigmoid + 0.5 threshold for two classes, softmax + argmax otherwise)."""
+    if num_classes == 2:
+        probs = torch.sigmoid(outputs.float()).cpu().numpy()
+        if probs.ndim == 1:
+            probs = np.column_stack((1 - probs, probs))
+        pred = (probs > 0.5).astype(int)
+        if pred.ndim == 1:
+            pred = pred[:, 1]
+        elif pred.ndim == 2:
+            pred = pred[:, -1]
+        return probs, pred
+    probs = torch.softmax(outputs.float(), dim=1).cpu().numpy()
+    pred = torch.argmax(outputs, dim=1).cpu().numpy()
+    return probs, pred
+
+
+class WindowPredictor:
+    """Sliding-window inference service shaped like ``InferenceEngine.predict`` (nexar_inference.py:103-340), for one
+    decoded video already on the device: every frame goes through the val transform once, the model sees batches of
+    ``[b,3,window,cs,cs]`` windows (strided views of the per-frame result, made contiguous per batch only), and one
+    result dictionary per window comes back with the reference's keys plus the window position.
+
+    ``model``: any callable taking ``[b,3,T,cs,cs]`` and returning logits ``[b,num_classes]`` (the reference passes
+    ``frames.permute(0,4,1,2,3).float().to(device)``, :248; here the tensor is born on the device in that layout)."""
+
+    def __init__(self, model: Callable[[torch.Tensor], torch.Tensor], window: int = 16, stride: int = 8, batch_size: int = 8,
+                 num_classes: int = 3, transform: Optional[GpuVideoTransform] = None, out_dtype: torch.dtype = torch.float32):
+        self.model = model
+        self.batch_size = int(batch_size)
+        self.num_classes = int(num_classes)
+        self.swt = SlidingWindowTransform(window=window, stride=stride, transform=transform, out_dtype=out_dtype)
+
+    @torch.no_grad()
+    def predict(self, video_u8: torch.Tensor, video_path: str = "", fps: float = 30.0) -> List[Dict[str, Any]]:
+        view = self.swt.windows(video_u8)                              # [K,3,T,cs,cs] strided view
+        starts = sliding_window_starts(max(video_u8.shape[0], self.swt.window), self.swt.window, self.swt.stride)
+        results: List[Dict[str, Any]] = []
+        for lo in range(0, view.shape[0], self.batch_size):
+            batch = view[lo:lo + self.batch_size].contiguous()
+            probs, pred = classify_outputs(self.model(batch), self.num_classes)
+            for i in range(batch.shape[0]):
+                cls = int(pred[i])
+                results.append({
+                    "predicted_class": cls,
+                    "predicted_class_name": CLASS_MAP.get(cls, f"Class {cls}"),
+                    "probabilities": {CLASS_MAP.get(k, f"Class {k}"): float(probs[i, k]) for k in range(probs.shape[1])},
+                    "video_path": video_path,
+                    "window_start": starts[lo + i],
+                    "window_start_sec": starts[lo + i] / float(fps),
+                    "center_frame": starts[lo + i] + self.swt.window // 2,
+                })
+        return results
