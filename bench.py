@@ -341,9 +341,9 @@ def run_cfg4(args, rank, world, dev, out_dtype):
             "ms_per_video": ms,
             "windows": {"views_stride8": {"ms": ms, "windows": k},
                         "materialised_stride8": {"ms": ms_m8, "windows": int(m8.shape[0]), "extra_bytes": int(m8.numel() * esz),
-                                                 "by": "torch strided copy of the per-frame result"},
+                                                 "by": "nexar_gather_windows (whole-plane copies of the per-frame result)"},
                         "materialised_stride1": {"ms": ms_m1, "windows": int(m1.shape[0]), "extra_bytes": int(m1.numel() * esz),
-                                                 "by": "torch strided copy of the per-frame result"}},
+                                                 "by": "nexar_gather_windows (whole-plane copies of the per-frame result)"}},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                          "frac_of_8TBs_nominal": ach / 8000.0, "peak_kind": kind, "level": "step (every launch of the step)",
                          "algorithmic_bytes_per_step": bytes_alg, "traffic": None},

@@ -149,6 +149,13 @@ size_t nexar_workspace_bytes_for(const NexarPlan* plan, int32_t n_clips, int32_t
  * (2 * |dst_stride[1]| + (canvas - 1) * (|dst_stride[3]| + |dst_stride[4]|)); both return NEXAR_ERR_UNSUPPORTED. */
 int nexar_clip_transform(const NexarPlan* plan, const NexarTransformArgs* args);
 
+/* Materialised sliding windows for inference (extends the single centred window of nexar_inference.py:211-231 to the
+ * stride-s windows of BASELINE config 4).  `frames` holds the per-frame result of one video as [n_frames][3] planes of
+ * plane_bytes each (layout BTCHW of nexar_clip_transform); dst receives [n_windows][3][window] planes with
+ * dst[k][c][t] = frames[min(k * stride + t, n_frames - 1)][c] (the last frame repeats past the end, nexar_videos.py:429-433). */
+int nexar_gather_windows(const void* frames, int64_t n_frames, int64_t plane_bytes, int32_t window, int32_t stride,
+                         int64_t n_windows, void* dst, void* stream);
+
 /* Number of kernel launches the last nexar_clip_transform call on this thread enqueued. */
 int nexar_last_launch_count(void);
 

@@ -268,3 +268,63 @@ def test_window_predictor_is_predict_shaped():
         assert r["center_frame"] == r["window_start"] + 8 and r["video_path"] == "synthetic.mp4"
     p2, c2 = classify_outputs(torch.tensor([[-2.0], [3.0]]), num_classes=2)            # binary head (:251-259)
     assert p2.shape == (2, 1) and c2.tolist() == [0, 1]
+
+
+class _ReferenceShapedDataset(torch.utils.data.Dataset):
+    """The body of nexar_videos.NvidiaDashcamDataset.__getitem__ (:348-496) that matters here, line for line: decode,
+    CTHW view, ``self.transform(frames)``, THWC view, dict; any failure -> all-zeros clip (:479-489)."""
+
+    def __init__(self, specs, transform, need=6):
+        self.specs, self.transform, self.need = specs, transform, need
+
+    def __len__(self):
+        return len(self.specs)
+
+    def __getitem__(self, idx):
+        from vision_collision_detection_b200.synth import make_clip_np
+        try:
+            h, w, seed = self.specs[idx]
+            if h == 0:
+                raise IOError("broken video")
+            frames = torch.from_numpy(make_clip_np(self.need, h, w, seed, "dashcam"))
+            frames = frames.permute(3, 0, 1, 2)                  # :441
+            frames = self.transform(frames)                      # :445
+            frames = frames.permute(1, 2, 3, 0)                  # :451
+            return {"frames": frames, "sensor": torch.zeros(self.need, 4), "target": "Normal", "id": f"v{idx}"}
+        except Exception:
+            return {"frames": torch.zeros(self.need, 224, 224, 3), "sensor": torch.zeros(self.need, 4), "target": "Normal",
+                    "id": f"v{idx}"}
+
+
+@pytest.mark.parametrize("workers", [0, 2])
+def test_zero_line_deferred_drop_in_through_an_unmodified_loader(workers):
+    """The reference's Dataset lines, DataLoader(num_workers, pin_memory=True) with the DEFAULT collate, and the
+    trainers' consumer line, all unchanged; only the factory is the deferred GPU one.  Mixed resolutions and a failed
+    item in the batch; every clip against the oracle with the parameters its worker drew."""
+    from torch.utils.data import DataLoader
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.deferred import DeferredBatch
+    from vision_collision_detection_b200.synth import make_clip_np
+    kw = dict(mode="train", crop_size=56, enable_custom_augmentation=True, brightness_range=(0.9, 1.1),
+              contrast_range=(0.9, 1.1), saturation_range=(0.9, 1.1), rotation_range=(-5, 5))
+    tf = create_video_transforms(**kw, deferred=True)
+    specs = [(96, 160, 1), (96, 160, 2), (0, 0, 0), (120, 90, 3), (96, 160, 4), (120, 90, 5)]
+    loader = DataLoader(_ReferenceShapedDataset(specs, tf), batch_size=3, shuffle=False, num_workers=workers, pin_memory=True)
+    cfg = O.TransformConfig(mode="train", crop_size=56, enable_custom_augmentation=True, aug=O.AugConfig(rotation_range=(-5, 5)))
+    seen = 0
+    for bi, batch in enumerate(loader):
+        fb = batch["frames"]
+        assert isinstance(fb, DeferredBatch) and fb.is_pinned() and tuple(fb.shape) == (3, 6, 56, 56, 3)
+        x = batch["frames"].permute(0, 4, 1, 2, 3).float().to(torch.device("cuda"))      # nexar_train.py:1139 / dvc:708
+        assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape) == (3, 3, 6, 56, 56)
+        got = x.cpu().numpy()
+        for g in fb.groups:
+            for pos, params in zip(g["index"], g["params"]):
+                h, w, seed = specs[bi * 3 + pos]
+                clip = make_clip_np(6, h, w, seed, "dashcam")
+                want = O.apply_clip_transform(clip.transpose(3, 0, 1, 2), cfg, {"flip": params["flip"], "aug": params["aug"]})
+                assert np.abs(got[pos] - want).max() <= TOL_AFTER
+                seen += 1
+        if bi == 0:
+            assert np.all(got[2] == 0)                                                   # the failed item stays zeros
+    assert seen == 5

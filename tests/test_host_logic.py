@@ -332,3 +332,44 @@ def test_reference_import_shims():
                 sys.modules[k] = v
             else:
                 sys.modules.pop(k, None)
+
+
+def test_deferred_transform_bookkeeping_without_cuda():
+    """The zero-line drop-in (deferred.py): inside the Dataset the transform returns a DeferredClip that follows the
+    reference's own lines (permute -> default_collate -> pin -> permute / float), nothing touches the GPU before .to()."""
+    import pickle
+    import random
+
+    from torch.utils.data import default_collate
+
+    from vision_collision_detection_b200 import GpuVideoTransform, create_video_transforms
+    from vision_collision_detection_b200.deferred import DeferredBatch, DeferredClip
+    tf = create_video_transforms(mode="train", enable_custom_augmentation=True, rotation_range=(-5, 5), deferred=True)
+    assert GpuVideoTransform.from_spec(tf.spec()).spec() == tf.spec() and hash(tf.spec()) is not None
+    plain = create_video_transforms(mode="train", enable_custom_augmentation=True, rotation_range=(-5, 5))
+    random.seed(3)
+    want_params = plain.sample_params(3, 36, 64)                 # same generator, same order as three deferred calls
+    random.seed(3)
+    items = []
+    for i in range(3):
+        frames = torch.randint(0, 255, (4, 36, 64, 3), dtype=torch.uint8)
+        clip = tf(frames.permute(3, 0, 1, 2))                    # nexar_videos.py:441-445
+        assert isinstance(clip, DeferredClip) and tuple(clip.shape) == (3, 4, 224, 224) and clip.dtype == torch.float32
+        assert clip.params == want_params[i] and torch.equal(clip.frames, frames)
+        clip = clip.permute(1, 2, 3, 0)                          # :451
+        assert tuple(clip.shape) == (4, 224, 224, 3) and len(clip) == 4
+        items.append({"frames": clip, "sensor": torch.zeros(4, 4), "target": "Normal", "id": f"v{i}"})
+    items.insert(0, {"frames": torch.zeros(4, 224, 224, 3), "sensor": torch.zeros(4, 4), "target": "Normal", "id": "bad"})
+    batch = default_collate(items)                               # the failed item comes first: the tensor hook delegates
+    fb = batch["frames"]
+    assert isinstance(fb, DeferredBatch) and tuple(fb.shape) == (4, 4, 224, 224, 3) and batch["id"] == ["bad", "v0", "v1", "v2"]
+    assert tuple(batch["sensor"].shape) == (4, 4, 4)             # ordinary tensors still collate as before
+    assert len(fb.groups) == 1 and fb.groups[0]["index"] == [1, 2, 3] and tuple(fb.groups[0]["frames"].shape) == (3, 4, 36, 64, 3)
+    x = fb.permute(0, 4, 1, 2, 3).float()                        # the consumer line, up to .to(device)
+    assert tuple(x.shape) == (4, 3, 4, 224, 224) and x._order == (0, 1, 2, 3, 4)
+    again = pickle.loads(pickle.dumps(fb))                       # worker -> main process
+    assert tuple(again.shape) == tuple(fb.shape) and again.groups[0]["params"] == fb.groups[0]["params"]
+    with pytest.raises(ValueError):
+        fb.permute(0, 1, 2, 3, 3)
+    with pytest.raises(TypeError):
+        default_collate([items[1]["frames"], torch.ones(4, 224, 224, 3)])      # only all-zeros fallbacks may be mixed in

@@ -117,6 +117,7 @@ def lib():
     L.nexar_workspace_bytes_for.restype = C.c_size_t
     L.nexar_clip_transform.argtypes = [C.c_void_p, C.POINTER(TransformArgs)]
     L.nexar_last_launch_count.restype = C.c_int
+    L.nexar_gather_windows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     L.nexar_set_resize_kernel.argtypes = [C.c_int32]
     L.nexar_set_fast_bands.argtypes = [C.c_int32]
     L.nexar_set_geometry_kernel.argtypes = [C.c_int32]

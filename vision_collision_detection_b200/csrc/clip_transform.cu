@@ -2456,6 +2456,49 @@ static int launch_chunked(const NexarPlan* p, const NexarTransformArgs* a, const
   return NEXAR_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Materialised sliding windows (BASELINE config 4): the val chain is per frame, so a video is transformed once into
+// [N][3][cs][cs] planes and window k = frames k*stride .. k*stride+window-1 (the last frame repeated past the end,
+// nexar_videos.py:429-433).  dst[k][c][t] = frames[min(k*stride + t, N-1)][c]: whole-plane copies, 16 bytes per thread.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_windows_kernel(const unsigned char* __restrict__ frames, long long n_frames, long long plane_bytes,
+                                                             int window, int stride, unsigned char* __restrict__ dst) {
+  const long long plane = blockIdx.x;              // (k * 3 + c) * window + t
+  const int t = (int)(plane % window);
+  const long long kc = plane / window;
+  const int c = (int)(kc % 3);
+  const long long k = kc / 3;
+  long long f = k * stride + t;
+  if (f > n_frames - 1) f = n_frames - 1;
+  const unsigned char* s = frames + (f * 3 + c) * plane_bytes;
+  unsigned char* d = dst + plane * plane_bytes;
+  const long long lo = (long long)blockIdx.y * plane_bytes / gridDim.y, hi = (long long)(blockIdx.y + 1) * plane_bytes / gridDim.y;
+  if ((plane_bytes & 15) == 0 && (lo & 15) == 0 && (hi & 15) == 0 && ((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
+    const uint4* s4 = (const uint4*)(s + lo);
+    uint4* d4 = (uint4*)(d + lo);
+    const long long n4 = (hi - lo) >> 4;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) __stcs(d4 + i, __ldg(s4 + i));   // the result is written once: streaming store
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = s[i];
+  }
+}
+
+extern "C" int nexar_gather_windows(const void* frames, int64_t n_frames, int64_t plane_bytes, int32_t window, int32_t stride,
+                                    int64_t n_windows, void* dst, void* stream) {
+  if (!frames || !dst || n_frames <= 0 || plane_bytes <= 0 || window <= 0 || stride <= 0 || n_windows <= 0)
+    return fail(NEXAR_ERR_INVALID, "gather_windows: bad argument");
+  const int64_t planes = n_windows * 3 * window;
+  if (planes > 2147483647LL) return fail(NEXAR_ERR_UNSUPPORTED, "gather_windows: more than 2^31 planes");
+  // each plane is split over `split` CTAs so that short videos still fill the machine; splits fall on 16-byte boundaries
+  int split = 1;
+  while (split < 8 && planes * split < 4 * (int64_t)sm_count() && (plane_bytes / (2 * split)) % 16 == 0 && plane_bytes / (2 * split) >= 4096) split *= 2;
+  gather_windows_kernel<<<dim3((unsigned)planes, split), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)frames, n_frames, plane_bytes,
+                                                                                       window, stride, (unsigned char*)dst);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return NEXAR_OK;
+}
+
 extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs* a) {
   g_launches = 0;
   if (!p || !a) return fail(NEXAR_ERR_INVALID, "clip_transform: null argument");

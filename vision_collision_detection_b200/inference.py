@@ -17,6 +17,7 @@ from typing import Any, Callable, Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _lib
 from .video_aug import GpuVideoTransform, create_video_transforms
 from .videos import select_start_frame, window_indices
 
@@ -62,9 +63,15 @@ class SlidingWindowTransform:
         starts = sliding_window_starts(fr.shape[0], self.window, self.stride)
         k = len(starts)
         s = fr.stride()
-        view = fr.as_strided((k, 3, self.window, fr.shape[2], fr.shape[3]),
+        if materialize:            # whole-plane gather through the library (one launch, streaming stores)
+            out = torch.empty((k, 3, self.window, fr.shape[2], fr.shape[3]), dtype=fr.dtype, device=fr.device)
+            with torch.cuda.device(fr.device):
+                _lib.check(_lib.lib().nexar_gather_windows(fr.data_ptr(), fr.shape[0], fr.shape[2] * fr.shape[3] * fr.element_size(),
+                                                           self.window, self.stride, k, out.data_ptr(),
+                                                           torch.cuda.current_stream(fr.device).cuda_stream))
+            return out
+        return fr.as_strided((k, 3, self.window, fr.shape[2], fr.shape[3]),
                              (self.stride * s[0], s[1], s[0], s[2], s[3]))
-        return view.contiguous() if materialize else view
 
 
 CLASS_MAP = {0: "Normal", 1: "Near Collision", 2: "Collision"}      # nexar_inference.py:239

@@ -15,8 +15,10 @@ import types
 from typing import Dict
 
 
-def install(replace_video_aug: bool = False) -> Dict[str, types.ModuleType]:
-    """Register the shim modules in ``sys.modules``; returns them by name.  Idempotent."""
+def install(replace_video_aug: bool = False, deferred: bool = False) -> Dict[str, types.ModuleType]:
+    """Register the shim modules in ``sys.modules``; returns them by name.  Idempotent.  ``deferred=True`` makes the
+    shimmed ``nexar_video_aug.create_video_transforms`` build deferred transforms (deferred.py), which is what the
+    unmodified trainers need: their Datasets run in forked DataLoader workers."""
     from . import VideoAugmentation, create_video_transform, create_video_transforms
     from .videos import GpuDashcamDataset, GpuVideoDataset
 
@@ -34,7 +36,12 @@ def install(replace_video_aug: bool = False) -> Dict[str, types.ModuleType]:
         aug = types.ModuleType("nexar_video_aug")
         aug.__doc__ = "shim: the GPU factories under the reference's module name (nexar_video_aug.py:318,636)"
         aug.__nexar_b200_shim__ = True
-        aug.create_video_transforms = create_video_transforms
+        if deferred:
+            import functools
+            aug.create_video_transforms = functools.partial(create_video_transforms, deferred=True)
+            functools.update_wrapper(aug.create_video_transforms, create_video_transforms)
+        else:
+            aug.create_video_transforms = create_video_transforms
         aug.create_video_transform = create_video_transform
         aug.VideoAugmentation = VideoAugmentation
         sys.modules["nexar_video_aug"] = aug

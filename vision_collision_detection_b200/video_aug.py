@@ -50,8 +50,15 @@ class GpuVideoTransform(nn.Module):
     def __init__(self, *, mode: str, crop_size: int, normalize: bool, video_mean, video_std,
                  horizontal_flip_prob: float, video_aug: Optional[VideoAugmentation],
                  resize_short_side: Optional[int] = None, use_letterbox: bool = True, center_crop: bool = False,
-                 out_dtype: torch.dtype = torch.float32, device=None, output_device: str = "input"):
+                 out_dtype: torch.dtype = torch.float32, device=None, output_device: str = "input",
+                 deferred: bool = False):
         super().__init__()
+        self.deferred = bool(deferred)
+        if self.deferred:
+            if resize_short_side is not None:
+                raise ValueError("deferred=True supports the letterbox factory (create_video_transforms) only")
+            from .deferred import install_collate_hooks
+            install_collate_hooks()
         self.mode = mode
         self.crop_size = int(crop_size)
         self.normalize = bool(normalize)
@@ -82,6 +89,36 @@ class GpuVideoTransform(nn.Module):
     @property
     def _flips(self) -> bool:
         return self.mode == "train" and self.horizontal_flip_prob > 0
+
+    # -- picklable description (deferred clips carry it from the DataLoader worker to the process that owns the GPU) ----
+    _AUG_FIELDS = ("brightness_range", "contrast_range", "saturation_range", "hue_range", "rotation_range", "scale_range",
+                   "shear_range", "translate_range", "grayscale_prob", "noise_level", "blur_sigma", "cutout_prob",
+                   "cutout_count_range", "cutout_size_range", "color_inversion_prob", "solarization_prob",
+                   "solarization_threshold", "posterization_prob", "posterization_bits_range", "aug_probability")
+
+    def spec(self) -> Tuple:
+        """Hashable constructor arguments: ``GpuVideoTransform.from_spec(tf.spec())`` transforms like ``tf``."""
+        aug = None
+        if self.video_aug is not None:
+            aug = tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v)
+                        for k in self._AUG_FIELDS for v in [getattr(self.video_aug, k)])
+        return (("mode", self.mode), ("crop_size", self.crop_size), ("normalize", self.normalize),
+                ("video_mean", self.video_mean), ("video_std", self.video_std),
+                ("horizontal_flip_prob", self.horizontal_flip_prob), ("video_aug", aug),
+                ("resize_short_side", self.resize_short_side), ("use_letterbox", self.use_letterbox),
+                ("center_crop", self.center_crop))
+
+    _spec_cache: Dict[Tuple, "GpuVideoTransform"] = {}
+
+    @classmethod
+    def from_spec(cls, spec: Tuple) -> "GpuVideoTransform":
+        tf = cls._spec_cache.get(spec)
+        if tf is None:
+            kw = dict(spec)
+            if kw["video_aug"] is not None:
+                kw["video_aug"] = VideoAugmentation(**dict(kw["video_aug"]))
+            tf = cls._spec_cache[spec] = cls(**kw)
+        return tf
 
     # -- random decisions, reference order -------------------------------------------
     def _resized_hw(self, h: int, w: int) -> Tuple[int, int]:
@@ -236,6 +273,16 @@ class GpuVideoTransform(nn.Module):
         changed), on the input's device unless ``output_device='cuda'``."""
         if video.dim() != 4 or video.shape[0] != 3:
             raise ValueError(f"expected [3,T,H,W], got {tuple(video.shape)}")
+        if self.deferred and not video.is_cuda:
+            # host part only (this runs inside a DataLoader worker): the random decisions, in the reference's order, and
+            # the decoded frames; the pixel work happens at ``batch['frames']....to(device)`` (deferred.py)
+            from .deferred import DeferredClip
+            if video.dtype not in (torch.uint8, torch.float32):
+                video = video.float()
+            thwc = video.permute(1, 2, 3, 0).contiguous()        # a no-copy view when the memory is THWC
+            params = self.sample_params(1, thwc.shape[1], thwc.shape[2])[0]
+            self.last_params = [params]
+            return DeferredClip(thwc, params, self.spec(), self.crop_size)
         src_device = video.device
         if video.dtype not in (torch.uint8, torch.float32):
             video = video.float()                       # nexar_video_aug.py:811-812
@@ -260,9 +307,9 @@ def create_video_transforms(
         jpeg_quality=0, grayscale_prob=0.0, cutout_prob=0.0, cutout_count=(1, 3),
         cutout_size_range=(0.1, 0.2), color_inversion_prob=0.0, solarization_prob=0.0,
         posterization_prob=0.0, posterization_bits_range=(3, 6), solarization_threshold=0.5, debug=False,
-        *, out_dtype=torch.float32, device=None, output_device="input"):
-    """Same positional/keyword surface as nexar_video_aug.py:636-696; the three keyword-only
-    arguments after ``debug`` are GPU additions."""
+        *, out_dtype=torch.float32, device=None, output_device="input", deferred=False):
+    """Same positional/keyword surface as nexar_video_aug.py:636-696; the keyword-only arguments after ``debug``
+    are GPU additions (``deferred=True``: the zero-line DataLoader drop-in of deferred.py)."""
     aug = None
     if mode == 'train' and enable_custom_augmentation:
         aug = VideoAugmentation(                      # exactly the kwargs forwarded at :762-788
@@ -274,7 +321,7 @@ def create_video_transforms(
             solarization_prob=solarization_prob, posterization_prob=posterization_prob, debug=debug)
     return GpuVideoTransform(mode=mode, crop_size=crop_size, normalize=normalize, video_mean=video_mean,
                              video_std=video_std, horizontal_flip_prob=horizontal_flip_prob, video_aug=aug,
-                             out_dtype=out_dtype, device=device, output_device=output_device)
+                             out_dtype=out_dtype, device=device, output_device=output_device, deferred=deferred)
 
 
 def create_video_transform(
