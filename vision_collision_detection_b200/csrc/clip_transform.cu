@@ -417,6 +417,7 @@ static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
 static const int kMaxBands = 16;
+constexpr unsigned kFrameReady = 0x80000000u;   // frame_done value once the frame's FrameInfo has been published
 
 
 // Per-frame constants computed once by K1.5 (frame_stats_kernel) so that K2/K3 start with a few 16-byte loads
@@ -498,6 +499,7 @@ struct KArgs {
   unsigned* clip_max;
   unsigned* frame_done;
   int finfo_by_k1;  // the fast resize kernel publishes the FrameInfo of every frame itself (K1.5 folded into K1)
+  int overlap;      // the colour kernel was launched as a programmatic dependent of the resize kernel: it polls frame_done
   unsigned long long* gray_partial;
   FrameInfo* finfo;
   uint2* inter;
@@ -880,6 +882,9 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
   __shared__ __align__(8) unsigned long long rowbar;  // "row staged" barrier: one arrival per warp, waited on one pair later
   constexpr int LA = NEXAR_LOOKAHEAD;  // row pairs ahead pushed into L2 by the bulk-prefetch engine (multiple of 4)
   const int tid = threadIdx.x;
+  // Programmatic dependent launch: the colour kernel's CTAs may be scheduled as soon as every CTA of this grid has
+  // started, i.e. into the SM slots this grid's last wave leaves empty; they synchronise per frame through frame_done.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int frame = blockIdx.y;
   const int clip = frame / A.T;
   const int t = frame - clip * A.T;
@@ -1139,6 +1144,8 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       if (atomicAdd(&A.frame_done[frame], 1u) == (unsigned)nb - 1u) {
         __threadfence();
         write_frame_info(P, A, frame, 0, nb);
+        __threadfence();
+        atomicExch(&A.frame_done[frame], kFrameReady);   // published: intermediate rows, clip flag and FrameInfo are visible
       }
     }
   }
@@ -1245,14 +1252,47 @@ constexpr int kColourPerThread = 8;
 #ifndef NEXAR_COL_MINB
 #define NEXAR_COL_MINB 6
 #endif
+// Wait until the resize kernel has published a frame (overlapped launch only).  Bounded: a stuck wait traps instead of
+// hanging the device.
+__device__ __forceinline__ void wait_frame_ready(const unsigned* flag) {
+  unsigned v;
+  for (int spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == kFrameReady) return;
+    __nanosleep(256);
+    if (spins > (1 << 22)) __trap();
+  }
+}
+
 __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
-  // K1 wrote the frames in ascending order, so the LAST ones are still in L2: walk them in descending order (and
-  // K3 then starts with frame 0, which this kernel wrote last)
-  const int frame = (int)(gridDim.y - 1u - blockIdx.y);
+  __shared__ unsigned go;
+  int frame;
+  if (A.overlap) {
+    // Launched as a programmatic dependent of the resize kernel: these CTAs fill the SM slots its last wave leaves
+    // empty, oldest frames first (almost always published already), and wait per frame for the publication.
+    frame = (int)blockIdx.y;
+    if (threadIdx.x == 0) {
+      const int clip = frame / A.T;
+      wait_frame_ready(A.frame_done + frame);
+      unsigned run = 1u;
+      if (A.pass == 4 && __ldcg(A.clip_max + clip) == 0u) {  // the clip flag is final only once all its frames are in
+        for (int f = clip * A.T; f < (clip + 1) * A.T; ++f) wait_frame_ready(A.frame_done + f);
+        run = __ldcg(A.clip_max + clip) != 0u;               // still 0: fixup_frame_kernel finishes that clip on its own
+      }
+      go = run;
+    }
+    __syncthreads();
+    if (!go) return;
+  } else {
+    // K1 wrote the frames in ascending order, so the LAST ones are still in L2: walk them in descending order (and
+    // K3 then starts with frame 0, which this kernel wrote last)
+    frame = (int)(gridDim.y - 1u - blockIdx.y);
+  }
   const float4* fi4 = (const float4*)(A.finfo + frame);
-  const float4 st = __ldg(fi4), q3 = __ldg(fi4 + 3), q4 = __ldg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, 6 * hue, -
+  // coherent loads (L2): in the overlapped launch the producer may still be running on other SMs
+  const float4 st = __ldcg(fi4), q3 = __ldcg(fi4 + 3), q4 = __ldcg(fi4 + 4);   // pad colour + cmean | g4, g5, flags, contrast | sat, sat_q, 6 * hue, -
   if (!(__float_as_uint(q3.z) & NEXAR_AUG)) return;
-  if (A.pass == 4 && A.clip_max[frame / A.T] == 0u) return;  // fixup_frame_kernel finishes those clips on its own
+  if (!A.overlap && A.pass == 4 && A.clip_max[frame / A.T] == 0u) return;  // fixup_frame_kernel finishes those clips on its own
   ColourParams c;
   c.cmean = st.w;
   c.contrast = q3.w;
@@ -1265,7 +1305,7 @@ __global__ void __launch_bounds__(256, NEXAR_COL_MINB) colour_kernel(const __gri
   uint2 v[kColourPerThread];
 #pragma unroll
   for (int k = 0; k < kColourPerThread; ++k)
-    if (i0 + k * 256 < n) v[k] = base[i0 + k * 256];
+    if (i0 + k * 256 < n) v[k] = __ldcg(base + i0 + k * 256);
 #pragma unroll
   for (int k = 0; k < kColourPerThread; ++k)
     if (i0 + k * 256 < n) {
@@ -2296,13 +2336,30 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
                         K.src_row_stride % 16 == 0 && ((uintptr_t)K.src % 16) == 0;
   bool tail_done = false;  // K2 / K3's work has already been enqueued
   int nbands = 1;
+  cudaError_t tail_err = cudaSuccess;
   auto launch_tail = [&]() {  // K1.5 + K2 + K3 (K.pass == 4: only the clips whose maximum was > 1)
     const int cs = P.cs;
     if (!K.finfo_by_k1) {
       frame_stats_kernel<<<(nf + 127) / 128, 128, 0, st>>>(P, K, nbands);
       ++g_launches;
     }
-    colour_kernel<<<dim3((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf), 256, 0, st>>>(P, K);
+    {
+      const dim3 cgrid((K.bh * K.bw + 256 * kColourPerThread - 1) / (256 * kColourPerThread), nf);
+      // Right behind the fast resize kernel the colour kernel is a PROGRAMMATIC DEPENDENT launch: its CTAs start in the
+      // SM slots the resize grid's last wave leaves empty and wait per frame for that frame's publication.
+      K.overlap = K.finfo_by_k1 && K.pass == 4 && g_resize_variant != 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = cgrid;
+      cfg.blockDim = dim3(256);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = K.overlap ? 1 : 0;
+      tail_err = cudaLaunchKernelEx(&cfg, colour_kernel, P, K);   // checked by the caller (this lambda returns nothing)
+      K.overlap = 0;
+    }
     // the two production geometries (720p -> 224 and 720p / 1080p -> 320 letterboxes) writing a planar row-contiguous
     // tensor take the specialised kernel; everything else the general one
     const bool planar = K.sx == 1 && K.sy == cs && K.st == (int64_t)cs * cs && g_geo_variant != 1;
@@ -2423,6 +2480,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     blur_kernel<DstT><<<dim3((cs * cs + 255) / 256, nf), 256, 0, st>>>(P, K);
     ++g_launches;
   }
+  CUDA_TRY(tail_err);
   CUDA_TRY(cudaGetLastError());
   return NEXAR_OK;
 }
@@ -2556,6 +2614,7 @@ extern "C" int nexar_clip_transform(const NexarPlan* p, const NexarTransformArgs
   K.clip_max = w.clip_max;
   K.frame_done = w.frame_done;
   K.finfo_by_k1 = 0;
+  K.overlap = 0;
   K.gray_partial = w.gray_partial;
   K.finfo = w.finfo;
   K.inter = w.inter;
