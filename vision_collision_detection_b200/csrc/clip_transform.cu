@@ -1256,11 +1256,17 @@ constexpr int kColourPerThread = 8;
 // hanging the device.
 __device__ __forceinline__ void wait_frame_ready(const unsigned* flag) {
   unsigned v;
-  for (int spins = 0;; ++spins) {
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0;; ++spins) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     if (v == kFrameReady) return;
     __nanosleep(256);
-    if (spins > (1 << 22)) __trap();
+    if ((spins & 4095u) == 4095u) {   // about once a millisecond: give up after 30 s of wall time (the producer is resident
+      unsigned long long now;        // and running whenever a consumer CTA exists, so this only fires on a broken device)
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0ull) t0 = now;
+      else if (now - t0 > 30000000000ull) __trap();
+    }
   }
 }
 
@@ -1649,6 +1655,9 @@ __global__ void __launch_bounds__(256) fixup_frame_kernel(const __grid_constant_
   __shared__ unsigned long long red[32];
   const int frame = blockIdx.x;
   const int clip = frame / A.T;
+  // launched as a programmatic dependent of the resize kernel itself (batches without augmentation): the clip flags are
+  // final only when that grid has completed
+  if (A.overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (A.clip_max[clip] != 0u) return;
   resize_general_body<SrcT, DstT>(P, A, frame, 0, 1, vbuf, red);  // A.pass == 1: unscaled, gray sum in slot 1
   const NexarClipParams* cp = A.params + clip;
@@ -1688,6 +1697,7 @@ constexpr int kGeoFrames = NEXAR_GEO_FRAMES;  // frames of one clip per CTA
 constexpr int kGeoPasses = NEXAR_GEO_PASSES;
 template <typename DstT, bool TAIL>
 __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
+  asm volatile("griddepcontrol.launch_dependents;");   // the fix-up launch may drain through this grid's last wave
   const int nchunk = (A.T + kGeoFrames - 1) / kGeoFrames;
   const int clip = blockIdx.z / nchunk;
   const int t0 = (blockIdx.z - clip * nchunk) * kGeoFrames, t1 = min(A.T, t0 + kGeoFrames);
@@ -1927,6 +1937,7 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
   constexpr int NF = NEXAR_GEO2_FRAMES;
   constexpr int FPX = BH * BW;   // pixels of one intermediate frame
   constexpr int OPX = CS * CS;   // elements of one output plane
+  asm volatile("griddepcontrol.launch_dependents;");   // the fix-up launch may drain through this grid's last wave
   const int ngroup = (A.T + NF - 1) / NF;
   const int clip = blockIdx.z / ngroup;
   const int t0 = (blockIdx.z - clip * ngroup) * NF;
@@ -2446,7 +2457,24 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     const size_t gsm = (size_t)P.src_w * 3 * sizeof(float);
     if (gsm > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(fixup_frame_kernel<SrcT, DstT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-    fixup_frame_kernel<SrcT, DstT><<<nf, 256, gsm, st>>>(P, K);
+    {
+      // Behind the geometry kernel the fix-up is a programmatic dependent launch too: it only needs the clip flags, which
+      // are final before the geometry kernel starts, and the two kernels write disjoint clips, so its (normally empty) CTAs
+      // drain through the geometry grid's last wave instead of costing a launch of their own.
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nf);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = gsm;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = (!fused && g_resize_variant != 2) ? 1 : 0;
+      K.overlap = cfg.numAttrs && !aug_mode;   // directly behind the resize kernel: wait for its completion on the device
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, fixup_frame_kernel<SrcT, DstT>, P, K));
+      K.overlap = 0;
+    }
     tail_done = true;
     g_launches += 2;
   } else {
