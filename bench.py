@@ -55,7 +55,7 @@ def ncu_traffic(workload, mode, out_dtype):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(f"{workload}:{mode}:{out_dtype}")
+            return json.load(f).get(f"{workload}:{mode}:{out_dtype}")     # {"step": bytes, "kernels": {name: bytes}}
     except Exception:
         return None
 
@@ -355,7 +355,7 @@ def run_cfg4(args, rank, world, dev, out_dtype):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -452,6 +452,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i)
+    t_enq = time.time()                  # the host has enqueued every step (the device is still working through them)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -564,10 +565,14 @@ def main():
                     "ms": k_ms, "achieved": k_ach, "frac": k_ach / peaks["hbm_gbs"], "share_of_step": k_ms / ms_step,
                     "timed": f"CUDA event pair around the launch on its stream (nexar_profile_begin/end), {k_steps} extra steps right after the timed region"}
         # roofline.frac is STEP level (all launches of the step, device events): it is never better than the kernel's own
+        traffic = ncu_traffic(args.workload, args.mode, args.out_dtype)
+        if kern and traffic:
+            kern["traffic"] = (traffic.get("kernels") or {}).get("resize_fast_kernel")
         roof = {"bound": "hbm", "achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_ach / peaks["hbm_gbs"],
                 "frac_of_8TBs_nominal": step_ach / 8000.0, "peak_kind": peak_kind, "level": "step (every launch of the step)",
                 "algorithmic_bytes_per_step": step_bytes, "kernel": kern,
-                "traffic": ncu_traffic(args.workload, args.mode, args.out_dtype)}
+                "traffic": (traffic or {}).get("step"), "traffic_by_kernel": (traffic or {}).get("kernels"),
+                "traffic_source": "profiles/traffic.json (ncu dram bytes per launch of this command, committed)" if traffic else None}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -585,6 +590,7 @@ def main():
                        "sharding": f"{b} clips per GPU, no collective" + (" (one 256-clip batch split over the GPUs)" if scaling == "strong" else ""),
                        "preheat": "60 ms of torch copies before the warm-up (clock ramp; not transform steps)"},
             "output_GBs": world * b * 3 * t * cs * cs * out.element_size() / (ms_step * 1e-3) / 1e9,
+            "host_enqueue_ms_per_step": 1e3 * (t_enq - t_wall0) / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_nv12": e2e_nv12, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

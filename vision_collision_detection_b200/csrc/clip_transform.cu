@@ -66,6 +66,7 @@ struct DevPlan {
   const int* xstart_al;    // [rw] even-aligned first tap
   const unsigned* xw16;    // [rw][kx_al / 2] the same taps in 15-bit fixed point, two per word: lo bytes | hi bytes << 16 (dp2a operand)
   int kx_al;
+  int x_align4;            // the horizontal windows start at multiples of four pixels (8-byte aligned: LDS.64, no bank conflicts at 4:1)
 };
 
 struct NexarPlan {
@@ -76,6 +77,7 @@ struct NexarPlan {
   std::vector<int> ystart, ycount, xstart, xcount;
   std::vector<float> ywt, xwt;
   bool fast_ok = false;
+  int x_align = 2;
   std::vector<uint4> pairs;
   std::vector<int> xstart_al;
   std::vector<float> xwt_al;
@@ -99,6 +101,14 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
   kx_al = kx + 1;
   kx_al = kx_al <= 10 ? 10 : kx_al <= 14 ? 14 : kx_al <= 20 ? 20 : 0;
   if (!kx_al) return false;
+  // Windows aligned to FOUR pixels (24 bytes of the staged row) when that still fits the tap budget: the horizontal pass
+  // then reads its window with 8-byte loads, and at an exact 4:1 scale (720p -> 320: lanes 6 words apart) those are
+  // conflict-free where the 4-byte loads of the 2-pixel alignment collide two ways on every access.
+  int align = 4;
+  for (int j = 0; j < g.resize_w; ++j)
+    if (p->xcount[j] + (p->xstart[j] & 3) > kx_al) align = 2;
+  if (kx_al != 10) align = 2;   // only the 10-tap kernels are instantiated with the 8-byte path
+  p->x_align = align;
   float wmax = 0.f;
   for (float w : p->ywt) wmax = w > wmax ? w : wmax;
   if (!(wmax > 0.f)) return false;
@@ -159,7 +169,7 @@ static bool build_fast_tables(NexarPlan* p, int ky, int kx, int& shift, int& kx_
   p->xstart_al.assign(g.resize_w, 0);
   p->xwt_al.assign((size_t)g.resize_w * kx_al, 0.f);
   for (int j = 0; j < g.resize_w; ++j) {
-    const int xs = p->xstart[j], al = xs & ~1, sh = xs - al;
+    const int xs = p->xstart[j], al = xs & ~(align - 1), sh = xs - al;
     p->xstart_al[j] = al;
     for (int k = 0; k < p->xcount[j]; ++k) p->xwt_al[(size_t)j * kx_al + k + sh] = p->xwt[(size_t)j * kx + k];
   }
@@ -393,6 +403,7 @@ extern "C" int nexar_plan_create(const NexarGeometry* g, int32_t src_dtype, Nexa
   d.xstart_al = p->fast_ok ? di + 2 * g->resize_h + 2 * g->resize_w : nullptr;
   d.xw16 = p->fast_ok ? (const unsigned*)(df + p->ywt.size() + p->xwt.size()) : nullptr;
   d.kx_al = kx_al;
+  d.x_align4 = p->fast_ok && p->x_align == 4;
   *out = p;
   return NEXAR_OK;
 }
@@ -874,7 +885,7 @@ __device__ __forceinline__ void write_frame_info(const DevPlan& P, const KArgs& 
 // FUSED: the nb bands of a frame form one thread-block cluster; after the resize the cluster goes on, in the same
 // launch, with the colour chain (in place on the band's own rows) and the affine gather + store (see
 // fused_colour_geometry), so the augmented path is ONE kernel and the intermediate is consumed while it is L2-hot.
-template <int KX, int NT, int MINB, int RS, typename DstT, bool FUSED>
+template <int KX, int NT, int MINB, int RS, typename DstT, bool FUSED, bool AL4>
 __global__ void __launch_bounds__(NT, MINB)
 resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1021,8 +1032,16 @@ resize_fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ KA
       /* the high tap bytes; value * 2^15 * sum(taps) = hi * 256 + lo (< 2^31) */                     \
       unsigned rl = 0u, rh = 0u, gl = 0u, gh = 0u, bl_ = 0u, bh = 0u;                                  \
       uint4 wq = wsm[tid];                                                                             \
+      unsigned wv[AL4 ? 3 * NW + 1 : 1]; /* AL4: the whole window, fetched with 8-byte loads */        \
+      if constexpr (AL4) {                                                                             \
+        _Pragma("unroll") for (int k = 0; k < (3 * NW + 1) / 2; ++k) {                                 \
+          const uint2 t_ = ((const uint2*)src)[k];                                                     \
+          wv[2 * k] = t_.x; wv[2 * k + 1] = t_.y;                                                      \
+        }                                                                                              \
+      }                                                                                                \
       _Pragma("unroll") for (int m = 0; m < NW; ++m) {                                                 \
-        const unsigned w0 = src[3 * m], w1 = src[3 * m + 1], w2 = src[3 * m + 2];                      \
+        const unsigned w0 = AL4 ? wv[3 * m] : src[3 * m], w1 = AL4 ? wv[3 * m + 1] : src[3 * m + 1],   \
+                       w2 = AL4 ? wv[3 * m + 2] : src[3 * m + 2];                                      \
         const unsigned ww = (m & 3) == 0 ? wq.x : (m & 3) == 1 ? wq.y : (m & 3) == 2 ? wq.z : wq.w;    \
         const unsigned rr = __byte_perm(w0, w1, 0x7610), gg = __byte_perm(w0, w2, 0x5432),             \
                        bb = __byte_perm(w1, w2, 0x7610);                                               \
@@ -2425,10 +2444,13 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     if (prof) cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
 #define NEXAR_FAST_RS(KXV, NTV, MB, RSV)                                                                          \
   {                                                                                                               \
+    constexpr bool kAl = (KXV) == 10;  /* 8-byte window loads exist for the 10-tap kernels only */                \
     if (fused)                                                                                                    \
-      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, true>, grid, NTV, smem_fast, st, nbands, P, K)); \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, true, false>, grid, NTV, smem_fast, st, nbands, P, K)); \
+    else if (kAl && P.x_align4)                                                                                   \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, false, kAl>, grid, NTV, smem_fast, st, 0, P, K)); \
     else                                                                                                          \
-      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, false>, grid, NTV, smem_fast, st, 0, P, K)); \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, false, false>, grid, NTV, smem_fast, st, 0, P, K)); \
   }
 #define NEXAR_FAST(KXV, NTV, MB) NEXAR_FAST_RS(KXV, NTV, MB, 0)
 // tightly packed 720p / 1080p rows get the row stride as a compile-time constant (immediate load offsets)
