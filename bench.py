@@ -548,6 +548,9 @@ def main():
         e2e["note"] = ("uint8 RGB over PCIe (the frames the reference's decoder delivers) bounds this leg; e2e_nv12 is the same "
                        "call fed with decoder surfaces (half the bytes), DESIGN.md F1")
         e2e_nv12 = run_e2e("nv12")
+        if world > 1:
+            e2e["note"] += ("; multi-GPU: h2d_GBs_per_gpu lists every rank's own rate - on a single-socket host the aggregate "
+                            "saturates (about 190 GB/s on the 8 x B200 box of DESIGN.md section 6), which is what bounds this leg")
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -574,7 +577,7 @@ def main():
                 "traffic": (traffic or {}).get("step"), "traffic_by_kernel": (traffic or {}).get("kernels"),
                 "traffic_source": "profiles/traffic.json (ncu dram bytes per launch of this command, committed)" if traffic else None}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # the CPU legs run on rank 0 of a single-GPU run only
             cores = os.cpu_count() or 1
             best, legs = cpu_legs(args.mode, t, h, w, cs, args.cpu_seconds)
             cpu = {"value": best, "unit": "clips/s", "cores": cores, "kind": "port",
