@@ -853,18 +853,35 @@ __device__ __forceinline__ uint2 pack_q21(float r, float g, float b) {
   const unsigned qb = __float_as_uint(fmaf(b, kQ21, 8388608.0f)) & 0x1FFFFFu;
   return make_uint2(qr | (qg << 21), (qg >> 11) | (qb << 10));
 }
+#ifndef NEXAR_STAGE2_Q16
+#define NEXAR_STAGE2_Q16 0   // measured: I2F.U16 runs on the quarter-rate conversion pipe, the geometry kernel gets 20 % slower
+#endif
+#if NEXAR_STAGE2_Q16
+// Stage 2 as plain uint16 = round(v * 65535).  A sample is unpacked by ONE conversion instruction that reads a 16-bit half
+// of the register directly (I2F.U16 Rd, Rs.H0 / .H1): no byte permute, and it runs on the conversion pipe instead of the
+// ALU pipe that bounds the geometry kernel.  value = U / 65535.
+constexpr float kQ15 = 65535.0f;
+constexpr float kQ15Magic = 8388608.0f;             // low 16 bits of float_bits(v * 65535 + 2^23) = round(v * 65535)
+constexpr float kS2Inv = 1.0f / 65535.0f;           // sum_content(w * v) = kS2Inv * sum(w * U) + kS2Off * sum(w)
+constexpr float kS2Off = 0.0f;
+__device__ __forceinline__ float q15_r(uint2 v) { return (float)(unsigned short)(v.x & 0xFFFFu); }
+__device__ __forceinline__ float q15_g(uint2 v) { return (float)(unsigned short)(v.x >> 16); }
+__device__ __forceinline__ float q15_b(uint2 v) { return (float)(unsigned short)(v.y & 0xFFFFu); }
+#else
 constexpr float kQ15 = 32767.0f;
 constexpr float kQ15Magic = 8388608.0f + 32768.0f;  // low 16 bits of float_bits(v * 32767 + magic) = 0x8000 | round(v * 32767)
-constexpr float kQ15Inv = 32768.0f / 32767.0f;      // v = (F - 1) * kQ15Inv
+constexpr float kS2Inv = 32768.0f / 32767.0f;       // v = (F - 1) * kS2Inv: sum_content(w * v) = kS2Inv * sum(w * F) + kS2Off * sum(w)
+constexpr float kS2Off = -kS2Inv;
+__device__ __forceinline__ float q15_r(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7104)); }
+__device__ __forceinline__ float q15_g(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7324)); }
+__device__ __forceinline__ float q15_b(uint2 v) { return __uint_as_float(__byte_perm(v.y, 0x3F000000u, 0x7104)); }
+#endif
 __device__ __forceinline__ uint2 pack_q15(float r, float g, float b) {
   const unsigned qr = __float_as_uint(fmaf(r, kQ15, kQ15Magic));
   const unsigned qg = __float_as_uint(fmaf(g, kQ15, kQ15Magic));
   const unsigned qb = __float_as_uint(fmaf(b, kQ15, kQ15Magic));
   return make_uint2(__byte_perm(qr, qg, 0x5410), qb & 0xFFFFu);
 }
-__device__ __forceinline__ float q15_r(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7104)); }
-__device__ __forceinline__ float q15_g(uint2 v) { return __uint_as_float(__byte_perm(v.x, 0x3F000000u, 0x7324)); }
-__device__ __forceinline__ float q15_b(uint2 v) { return __uint_as_float(__byte_perm(v.y, 0x3F000000u, 0x7104)); }
 
 // thread-block cluster barrier (all threads of all CTAs of the cluster); release/acquire at cluster scope orders the
 // global-memory writes before the arrive with the reads after the wait
@@ -1588,14 +1605,14 @@ __device__ __forceinline__ void fused_colour_geometry(const DevPlan& P, const KA
     const float sg = fmaf(q15_g(v11), q.w11, fmaf(q15_g(v10), q.w10, fmaf(q15_g(v01), q.w01, q15_g(v00) * q.w00)));
     const float sb = fmaf(q15_b(v11), q.w11, fmaf(q15_b(v10), q.w10, fmaf(q15_b(v01), q.w01, q15_b(v00) * q.w00)));
     if (cls == GEO_INTERIOR) {  // m = wc = 1
-      r = fmaf(sr, kQ15Inv, -kQ15Inv);
-      g = fmaf(sg, kQ15Inv, -kQ15Inv);
-      b = fmaf(sb, kQ15Inv, -kQ15Inv);
+      r = fmaf(sr, kS2Inv, kS2Off);
+      g = fmaf(sg, kS2Inv, kS2Off);
+      b = fmaf(sb, kS2Inv, kS2Off);
     } else {
-      const float t0 = -kQ15Inv * q.wc, pm = q.m - q.wc;
-      r = q.m * fmaf(sr, kQ15Inv, fmaf(padr, pm, t0));
-      g = q.m * fmaf(sg, kQ15Inv, fmaf(padg, pm, t0));
-      b = q.m * fmaf(sb, kQ15Inv, fmaf(padb, pm, t0));
+      const float t0 = kS2Off * q.wc, pm = q.m - q.wc;
+      r = q.m * fmaf(sr, kS2Inv, fmaf(padr, pm, t0));
+      g = q.m * fmaf(sg, kS2Inv, fmaf(padg, pm, t0));
+      b = q.m * fmaf(sb, kS2Inv, fmaf(padb, pm, t0));
     }
   };
 
@@ -1822,7 +1839,7 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
           g.w00 = g.wc = in ? 1.0f : 0.0f;
           g.w01 = g.w10 = g.w11 = 0.0f;
         }
-        t0q[e] = -kQ15Inv * g.wc;
+        t0q[e] = kS2Off * g.wc;
         pmq[e] = g.m - g.wc;
       }
     }
@@ -1853,13 +1870,13 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
           const float sg = fmaf(q15_g(v[e][3]), g.w11, fmaf(q15_g(v[e][2]), g.w10, fmaf(q15_g(v[e][1]), g.w01, q15_g(v[e][0]) * g.w00)));
           const float sb = fmaf(q15_b(v[e][3]), g.w11, fmaf(q15_b(v[e][2]), g.w10, fmaf(q15_b(v[e][1]), g.w01, q15_b(v[e][0]) * g.w00)));
           if (cls == GEO_INTERIOR) {  // m = wc = 1
-            rr[e] = fmaf(sr, kQ15Inv, -kQ15Inv);
-            gg[e] = fmaf(sg, kQ15Inv, -kQ15Inv);
-            bb[e] = fmaf(sb, kQ15Inv, -kQ15Inv);
+            rr[e] = fmaf(sr, kS2Inv, kS2Off);
+            gg[e] = fmaf(sg, kS2Inv, kS2Off);
+            bb[e] = fmaf(sb, kS2Inv, kS2Off);
           } else {
-            rr[e] = g.m * fmaf(sr, kQ15Inv, fmaf(padv.x, pmq[e], t0q[e]));
-            gg[e] = g.m * fmaf(sg, kQ15Inv, fmaf(padv.y, pmq[e], t0q[e]));
-            bb[e] = g.m * fmaf(sb, kQ15Inv, fmaf(padv.z, pmq[e], t0q[e]));
+            rr[e] = g.m * fmaf(sr, kS2Inv, fmaf(padv.x, pmq[e], t0q[e]));
+            gg[e] = g.m * fmaf(sg, kS2Inv, fmaf(padv.y, pmq[e], t0q[e]));
+            bb[e] = g.m * fmaf(sb, kS2Inv, fmaf(padv.z, pmq[e], t0q[e]));
           }
         }
       }
@@ -1932,6 +1949,9 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
 #ifndef NEXAR_GEO2_MINB
 #define NEXAR_GEO2_MINB 3
 #endif
+#ifndef NEXAR_GEO2_XU
+#define NEXAR_GEO2_XU 0      // channels (0..2: none, B, G + B) unpacked through the conversion pipe instead of the ALU pipe
+#endif
 #ifndef NEXAR_GEO2_WARPS
 #define NEXAR_GEO2_WARPS 8   // warps per CTA: the CTA tile is 32 x (4 * warps) pixels
 #endif
@@ -2001,9 +2021,18 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
   const int64_t osc = A.sc;
   const bool tail_fx = TAIL && (flags & kTailFlags) != 0u;
   const float nsr = A.nscale[0], nsg = A.nscale[1], nsb = A.nscale[2], nbr = A.nbias[0], nbg = A.nbias[1], nbb = A.nbias[2];
+  // Unpacking: a byte permute per sample (ALU pipe, which bounds this kernel) - except for NEXAR_GEO2_XU of the three
+  // channels, which go through I2F.U16 on the otherwise idle conversion pipe: the stored 0x8000 | q reads as 32768 * F there,
+  // and the factor goes into that channel's constants.
+  constexpr float kXg = (NEXAR_GEO2_XU >= 2 && !NEXAR_STAGE2_Q16) ? 1.0f / 32768.0f : 1.0f;
+  constexpr float kXb = (NEXAR_GEO2_XU >= 1 && !NEXAR_STAGE2_Q16) ? 1.0f / 32768.0f : 1.0f;
+  auto ur = [](uint2 v) { return q15_r(v); };
+  auto ug = [](uint2 v) { return kXg != 1.0f ? (float)(unsigned short)(v.x >> 16) : q15_g(v); };
+  auto ub = [](uint2 v) { return kXb != 1.0f ? (float)(unsigned short)(v.y & 0xFFFFu) : q15_b(v); };
+  constexpr float kInvR = kS2Inv, kInvG = kS2Inv * kXg, kInvB = kS2Inv * kXb;
   // interior class: out = s * (k * ns) + (nb - k * ns), s = sum(w * F), F = 1 + q / 32768, k = 32768 / 32767
-  const float kir = kQ15Inv * nsr, kig = kQ15Inv * nsg, kib = kQ15Inv * nsb;
-  const float cir = nbr - kir, cig = nbg - kig, cib = nbb - kib;
+  const float kir = kInvR * nsr, kig = kInvG * nsg, kib = kInvB * nsb;
+  const float cir = fmaf(kS2Off, nsr, nbr), cig = fmaf(kS2Off, nsg, nbg), cib = fmaf(kS2Off, nsb, nbb);
   const float xb = (float)x - half + 0.5f;
   const float xg0 = xb * g0, xg3 = xb * g3;
 
@@ -2060,7 +2089,7 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
           a00 = wA * hA; a01 = wB * hA; a10 = wA * hB; a11 = wB * hB;
           const float wc = (bx0w + bx1w) * (by0w + by1w);
           mq[e] = m;
-          t0q[e] = -kQ15Inv * wc;
+          t0q[e] = kS2Off * wc;
           pmq[e] = m - wc;
         }
         if (e == 0) { w00.x = a00; w01.x = a01; w10.x = a10; w11.x = a11; }
@@ -2115,18 +2144,18 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
         }
         const uint2* ca = va[f & 1];
         const uint2* cb = vb[f & 1];
-        float2 sr = fmul2(make_float2(q15_r(ca[0]), q15_r(cb[0])), w00);
-        float2 sg = fmul2(make_float2(q15_g(ca[0]), q15_g(cb[0])), w00);
-        float2 sb = fmul2(make_float2(q15_b(ca[0]), q15_b(cb[0])), w00);
-        sr = ffma2(make_float2(q15_r(ca[1]), q15_r(cb[1])), w01, sr);
-        sg = ffma2(make_float2(q15_g(ca[1]), q15_g(cb[1])), w01, sg);
-        sb = ffma2(make_float2(q15_b(ca[1]), q15_b(cb[1])), w01, sb);
-        sr = ffma2(make_float2(q15_r(ca[2]), q15_r(cb[2])), w10, sr);
-        sg = ffma2(make_float2(q15_g(ca[2]), q15_g(cb[2])), w10, sg);
-        sb = ffma2(make_float2(q15_b(ca[2]), q15_b(cb[2])), w10, sb);
-        sr = ffma2(make_float2(q15_r(ca[3]), q15_r(cb[3])), w11, sr);
-        sg = ffma2(make_float2(q15_g(ca[3]), q15_g(cb[3])), w11, sg);
-        sb = ffma2(make_float2(q15_b(ca[3]), q15_b(cb[3])), w11, sb);
+        float2 sr = fmul2(make_float2(ur(ca[0]), ur(cb[0])), w00);
+        float2 sg = fmul2(make_float2(ug(ca[0]), ug(cb[0])), w00);
+        float2 sb = fmul2(make_float2(ub(ca[0]), ub(cb[0])), w00);
+        sr = ffma2(make_float2(ur(ca[1]), ur(cb[1])), w01, sr);
+        sg = ffma2(make_float2(ug(ca[1]), ug(cb[1])), w01, sg);
+        sb = ffma2(make_float2(ub(ca[1]), ub(cb[1])), w01, sb);
+        sr = ffma2(make_float2(ur(ca[2]), ur(cb[2])), w10, sr);
+        sg = ffma2(make_float2(ug(ca[2]), ug(cb[2])), w10, sg);
+        sb = ffma2(make_float2(ub(ca[2]), ub(cb[2])), w10, sb);
+        sr = ffma2(make_float2(ur(ca[3]), ur(cb[3])), w11, sr);
+        sg = ffma2(make_float2(ug(ca[3]), ug(cb[3])), w11, sg);
+        sb = ffma2(make_float2(ub(ca[3]), ub(cb[3])), w11, sb);
         if (cls == GEO_INTERIOR) {  // m = wc = 1
           if (!tail_fx) {           // scale and normalisation in one multiply-add
             put(por, f, fmaf(sr.x, kir, cir), fmaf(sr.y, kir, cir));
@@ -2134,13 +2163,13 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
             put(pob, f, fmaf(sb.x, kib, cib), fmaf(sb.y, kib, cib));
             continue;
           }
-          rr = make_float2(fmaf(sr.x, kQ15Inv, -kQ15Inv), fmaf(sr.y, kQ15Inv, -kQ15Inv));
-          gg = make_float2(fmaf(sg.x, kQ15Inv, -kQ15Inv), fmaf(sg.y, kQ15Inv, -kQ15Inv));
-          bb = make_float2(fmaf(sb.x, kQ15Inv, -kQ15Inv), fmaf(sb.y, kQ15Inv, -kQ15Inv));
+          rr = make_float2(fmaf(sr.x, kInvR, kS2Off), fmaf(sr.y, kInvR, kS2Off));
+          gg = make_float2(fmaf(sg.x, kInvG, kS2Off), fmaf(sg.y, kInvG, kS2Off));
+          bb = make_float2(fmaf(sb.x, kInvB, kS2Off), fmaf(sb.y, kInvB, kS2Off));
         } else {
-          rr = make_float2(mq[0] * fmaf(sr.x, kQ15Inv, fmaf(padv.x, pmq[0], t0q[0])), mq[1] * fmaf(sr.y, kQ15Inv, fmaf(padv.x, pmq[1], t0q[1])));
-          gg = make_float2(mq[0] * fmaf(sg.x, kQ15Inv, fmaf(padv.y, pmq[0], t0q[0])), mq[1] * fmaf(sg.y, kQ15Inv, fmaf(padv.y, pmq[1], t0q[1])));
-          bb = make_float2(mq[0] * fmaf(sb.x, kQ15Inv, fmaf(padv.z, pmq[0], t0q[0])), mq[1] * fmaf(sb.y, kQ15Inv, fmaf(padv.z, pmq[1], t0q[1])));
+          rr = make_float2(mq[0] * fmaf(sr.x, kInvR, fmaf(padv.x, pmq[0], t0q[0])), mq[1] * fmaf(sr.y, kInvR, fmaf(padv.x, pmq[1], t0q[1])));
+          gg = make_float2(mq[0] * fmaf(sg.x, kInvG, fmaf(padv.y, pmq[0], t0q[0])), mq[1] * fmaf(sg.y, kInvG, fmaf(padv.y, pmq[1], t0q[1])));
+          bb = make_float2(mq[0] * fmaf(sb.x, kInvB, fmaf(padv.z, pmq[0], t0q[0])), mq[1] * fmaf(sb.y, kInvB, fmaf(padv.z, pmq[1], t0q[1])));
         }
       }
       if (tail_fx) {
