@@ -8,7 +8,6 @@ for mode in custom val; do
 done
 if [ -n "$CFG3" ]; then
 timeout 300 python bench.py --steps 20 --warmup 5 --workload cfg3 --mode custom --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg3.log 2>&1
-NEXAR_RESIZE_VARIANT=4 timeout 300 python bench.py --steps 20 --warmup 5 --workload cfg3 --mode custom --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg3_fused.log 2>&1
 fi
 if [ -n "$NCU" ]; then
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:${NCUK:-resize_fast} -s ${NCUS:-4} -c 1 -f -o gpurun_out/prof python bench.py --steps 3 --warmup 3 --mode ${NCU} --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1

@@ -235,6 +235,9 @@ extern "C" size_t nexar_sizeof_transform_args(void) { return sizeof(NexarTransfo
 extern "C" const char* nexar_last_error(void) { return g_err.c_str(); }
 extern "C" int nexar_last_launch_count(void) { return g_launches; }
 extern "C" int nexar_set_resize_kernel(int32_t v) {
+#ifndef NEXAR_WITH_FUSED_CLUSTER
+  if (v == 4) return fail(NEXAR_ERR_UNSUPPORTED, "set_resize_kernel: variant 4 needs a build with -DNEXAR_WITH_FUSED_CLUSTER");
+#endif
   g_resize_variant = v;
   return NEXAR_OK;
 }
@@ -2356,6 +2359,11 @@ static int sm_count() {  // of the current device (cached per device)
   return cached[dev];
 }
 
+#ifdef NEXAR_WITH_FUSED_CLUSTER
+constexpr bool kWithFused = true;
+#else
+constexpr bool kWithFused = false;   // the `fused` branch below is never taken; it then names the unfused instantiation
+#endif
 // launch of the fast resize kernel; cluster > 0: the `cluster` bands of a frame form one thread-block cluster (fused path)
 template <typename Kern>
 static cudaError_t launch_fast(Kern kern, dim3 grid, int nt, size_t smem, cudaStream_t st, int cluster, const DevPlan& P,
@@ -2456,7 +2464,11 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
     // Variant 4: augmented batches take the fused kernel, the bands of a frame being one cluster (1, 2, 4 or 8 CTAs).
     // Measured on B200 it is not faster than K1 + K2 + K3 (the SMs are issue-bound either way and K2 / K3 run at twice
     // the occupancy), so it is not the default; it does have the lowest DRAM traffic (1.12x algorithmic).
+#ifdef NEXAR_WITH_FUSED_CLUSTER
     const bool fused = aug_mode && g_resize_variant == 4;
+#else
+    const bool fused = false;   // the one-launch variant is compiled only with -DNEXAR_WITH_FUSED_CLUSTER (measured slower)
+#endif
     if (fused) {
       int c = 1;
       while (2 * c <= nbands && 2 * c <= 8) c *= 2;
@@ -2475,7 +2487,7 @@ static int launch_all(const NexarPlan* p, const NexarTransformArgs* a, KArgs& K,
   {                                                                                                               \
     constexpr bool kAl = (KXV) == 10;  /* 8-byte window loads exist for the 10-tap kernels only */                \
     if (fused)                                                                                                    \
-      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, true, false>, grid, NTV, smem_fast, st, nbands, P, K)); \
+      CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, kWithFused, false>, grid, NTV, smem_fast, st, nbands, P, K)); \
     else if (kAl && P.x_align4)                                                                                   \
       CUDA_TRY(launch_fast(resize_fast_kernel<KXV, NTV, MB, RSV, DstT, false, kAl>, grid, NTV, smem_fast, st, 0, P, K)); \
     else                                                                                                          \
