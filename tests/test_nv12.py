@@ -98,3 +98,31 @@ def test_host_pipeline_nv12():
     out = pipe.run(host, params=params).float().numpy().copy()
     want = tf.forward_batch(torch.from_numpy(N.nv12_to_rgb(nv.numpy())).cuda(), params=params).float().cpu().numpy()
     assert np.array_equal(out, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,pad", [(720, 1280, 64), (96, 160, 16), (90, 150, 7)])
+def test_nv12_padded_pitch_through_the_engine(h, w, pad):
+    """Decoder surfaces have a pitch: the C ABI takes it as src_row_stride (Y and UV planes share it).  16-byte pitches
+    of 16-pixel-multiple widths take the vector conversion kernel, everything else the 2 x 2 one; the padding bytes must
+    never be read (they are 255 here) and the result equals the packed surfaces' bit for bit."""
+    from vision_collision_detection_b200 import create_video_transforms
+    from vision_collision_detection_b200.engine import get_engine, _alloc_out
+    from vision_collision_detection_b200.params import pack_clip_params
+    t, cs = 2, 64
+    nv = torch.from_numpy(rgb_to_nv12(make_clip_np(t, h, w, 31, "dashcam"))).cuda()      # [t, h*3/2, w]
+    tf = create_video_transforms(mode="val", crop_size=cs)
+    want = tf.forward_batch(nv.unsqueeze(0), pixel_format="nv12").cpu().numpy()
+    eng = get_engine(nv.device)
+    plan = tf._plan(eng, h, w, "nv12")
+    pitch = w + pad
+    rows = h * 3 // 2
+    buf = torch.full((t, rows, pitch), 255, dtype=torch.uint8, device="cuda")
+    buf[:, :, :w] = nv
+    offsets = torch.arange(t, dtype=torch.int64, device="cuda") * (rows * pitch)
+    packed, any_flags = pack_clip_params(tf.last_params, cs, tf.video_aug)
+    out, strides = _alloc_out("BCTHW", 1, t, cs, torch.float32, nv.device)
+    eng.run(plan, buf, offsets, 1, t, eng.upload_params(packed), any_flags, out, strides,
+            tf.normalize, tf.video_mean, tf.video_std, src_row_stride=pitch)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)

@@ -11,6 +11,6 @@ for n in 2 4 8; do
 done
 timeout 300 $TR --nproc-per-node 8 --master-port 29520 tools/train_step_share.py --steps 10 > gpurun_out/mg_cfg5_n8.log 2>&1
 timeout 300 $TR --nproc-per-node 8 --master-port 29521 bench.py --gpus 8 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/mg_cfg2_n8.log 2>&1
-timeout 300 $TR --nproc-per-node 8 --master-port 29522 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline --no-numa-bind > gpurun_out/mg_cfg2_n8_nobind.log 2>&1
-timeout 300 $TR --nproc-per-node 4 --master-port 29523 bench.py --gpus 4 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/mg_cfg2_n4.log 2>&1
+timeout 300 $TR --nproc-per-node 4 --master-port 29523 bench.py --gpus 4 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/mg_cfg2_n4.log 2>&1
+timeout 300 $TR --nproc-per-node 2 --master-port 29524 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/mg_cfg2_n2.log 2>&1
 true
