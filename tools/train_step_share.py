@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sync-every-step", action="store_true", help="synchronize after every step (unoverlapped transform latency)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -69,9 +70,13 @@ def main():
     clips = torch.stack([make_clip_torch(args.frames, 720, 1280, rank * 100 + i, "dashcam", dev) for i in range(args.batch)])
     labels = torch.randint(0, 3, (args.batch,), device=dev)
     random.seed(1234 + rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    t_aug = t_step = 0.0
-    for i in range(args.warmup + args.steps):
+    # One event triple per step and a single synchronize at the end: like a real training loop the host runs ahead of the
+    # device, so ev[0] -> ev[1] is the time the DEVICE spends on the transform inside a step (the host-side parameter
+    # packing of step i+1 overlaps the model's kernels of step i); --sync-every-step gives the unoverlapped latency instead.
+    n_total = args.warmup + args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_total)]
+    for i in range(n_total):
+        ev = evs[i]
         ev[0].record()
         x = tf.forward_batch(clips)                                   # [B,3,T,224,224] fp32
         ev[1].record()
@@ -82,10 +87,11 @@ def main():
         scaler.step(opt)
         scaler.update()
         ev[2].record()
-        torch.cuda.synchronize()
-        if i >= args.warmup:
-            t_aug += ev[0].elapsed_time(ev[1])
-            t_step += ev[0].elapsed_time(ev[2])
+        if args.sync_every_step:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    t_aug = sum(ev[0].elapsed_time(ev[1]) for ev in evs[args.warmup:])
+    t_step = evs[args.warmup][0].elapsed_time(evs[-1][2])            # wall time of the timed steps on the device
     t = torch.tensor([t_aug, t_step], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -97,7 +103,7 @@ def main():
                                    "temporal_mode='gru') (nexar_arch.py:390-443), built from torchvision; NOT the reference class",
                           "aug": "nexar_videos.py:2003-2010 kwargs, device-resident uint8 720p clips -> fp32 [B,3,T,224,224]",
                           "n_gpus": world, "batch_per_gpu": args.batch, "frames": args.frames,
-                          "ms_aug": a, "ms_step": s, "aug_share": a / s, "clips_per_s": world * args.batch / (s * 1e-3)}))
+                          "ms_aug": a, "ms_step": s, "aug_share": a / s, "sync_every_step": bool(args.sync_every_step), "clips_per_s": world * args.batch / (s * 1e-3)}))
     if world > 1:
         dist.destroy_process_group()
 
