@@ -1950,13 +1950,13 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
 #define NEXAR_GEO2_FRAMES 8
 #endif
 #ifndef NEXAR_GEO2_MINB
-#define NEXAR_GEO2_MINB 3
+#define NEXAR_GEO2_MINB 6
 #endif
 #ifndef NEXAR_GEO2_XU
 #define NEXAR_GEO2_XU 0      // channels (0..2: none, B, G + B) unpacked through the conversion pipe instead of the ALU pipe
 #endif
 #ifndef NEXAR_GEO2_WARPS
-#define NEXAR_GEO2_WARPS 8   // warps per CTA: the CTA tile is 32 x (4 * warps) pixels
+#define NEXAR_GEO2_WARPS 4   // warps per CTA: the CTA tile is 32 x (4 * warps) pixels (3 / 4 / 5 / 8 measured: 4 is best by 1 %)
 #endif
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
