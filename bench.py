@@ -282,7 +282,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}:{args.mode} {t}x{h}x{w} u8 -> {cs}x{cs} f32 on host CPU"},
+        "config": {"workload": f"{args.workload}:{args.mode} {t}x{h}x{w} u8 -> {cs}x{cs}", "out_dtype": "f32", "where": "host CPU",
+                   "kwargs": "nexar_videos.py:2003-2010" if args.mode == "custom" else args.mode},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample_desc,
                          "probe_all_threads": probe, "probe_workers": wprobe},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -587,7 +588,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": f"u8 -> i32 fixed-point (15-bit taps) / f32 -> {args.out_dtype}", "data": "synthetic",
-            "config": {"workload": f"{args.workload}:{args.mode} {b} clips/GPU x {t}x{h}x{w} u8 -> {cs}x{cs} {args.out_dtype}",
+            "config": {"workload": f"{args.workload}:{args.mode} {t}x{h}x{w} u8 -> {cs}x{cs}", "out_dtype": args.out_dtype,
+                       "clips_per_gpu_per_step": b, "where": "B200, inputs resident in HBM",
                        "kwargs": "nexar_videos.py:2003-2010" if args.mode == "custom" else args.mode,
                        "l2": f"input {b * t * h * w * 3 / 1e9:.1f} GB/step > 126 MB L2 (no flush needed)",
                        "sharding": f"{b} clips per GPU, no collective" + (" (one 256-clip batch split over the GPUs)" if scaling == "strong" else ""),

@@ -4,9 +4,12 @@
 //   K1 resize   : uint8 THWC frames -> antialiased separable resample -> either the
 //                 final normalised tensor (no augmentation) or a brightness-adjusted
 //                 8-byte intermediate pixel + per-band gray sums (augmentation).
-//   K2 colour   : contrast (needs the frame's gray mean) -> saturation -> hue, in place.
-//   K3 geometry : affine gather with the fill=0 mask quirk, effects, normalise, store.
+//   K2 colour   : contrast (needs the frame's gray mean) -> saturation -> hue, in place; a programmatic dependent
+//                 launch of K1 that starts in K1's last wave and waits per frame on a publication flag.
+//   K3 geometry : affine gather with the fill=0 mask quirk, effects, normalise, store (a kernel specialised for the
+//                 production letterboxes, a general one for everything else).
 //   K4 blur     : only when blur_sigma > 0 (reflect-padded gaussian, then the rest of the chain).
+//   NV12 -> RGB : decoder surfaces converted in front of K1 (NEXAR_SRC_NV12); window gather for inference.
 // The /255 decision of VideoTransform.forward is clip-global and data dependent
 // (nexar_video_aug.py:814): K1 runs assuming "max > 1", records the clip maximum, and
 // a second, normally empty, launch (fixup_frame_kernel) redoes the clips whose maximum was <= 1.
@@ -28,9 +31,9 @@
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 // experiment knobs and the optional kernel timing are per calling thread (the library keeps no process-global mutable state)
-static thread_local int g_resize_variant = 0;  // 0 auto, 1 force the general fp32 kernels, 4 fused cluster kernel for augmented batches
+static thread_local int g_resize_variant = 0;  // 0 auto, 1 force the general fp32 kernels, 2 no programmatic overlap, 4 fused cluster kernel (optional build)
 static thread_local int g_fast_bands = 0;      // 0 auto
-static thread_local int g_chunk_clips = 0;     // clips per chunk of an augmented batch (0 auto)
+static thread_local int g_chunk_clips = 0;     // clips per chunk of an augmented batch (0: the whole batch at once)
 static thread_local int g_geo_variant = 0;     // 0 auto (specialised geometry kernel when the shape allows it), 1 force the general one
 
 static thread_local std::vector<cudaEvent_t> g_prof_ev;
