@@ -1955,6 +1955,9 @@ __global__ void __launch_bounds__(256, NEXAR_GEO_MINB) geometry_kernel(const __g
 #ifndef NEXAR_GEO2_MINB
 #define NEXAR_GEO2_MINB 6
 #endif
+#ifndef NEXAR_GEO2_AHEAD
+#define NEXAR_GEO2_AHEAD 0   // groups ahead whose frames the first tile column prefetches into L2 (0: off)
+#endif
 #ifndef NEXAR_GEO2_REVERSE
 #define NEXAR_GEO2_REVERSE 1   // measured: 0.3952 -> 0.3935 ms at cfg2
 #endif
@@ -1991,6 +1994,23 @@ __global__ void __launch_bounds__(32 * NEXAR_GEO2_WARPS, NEXAR_GEO2_MINB) geomet
   const int bz = (int)(gridDim.z - 1u - blockIdx.z);   // last frame groups first: the colour kernel wrote them last (L2)
 #else
   const int bz = (int)blockIdx.z;
+#endif
+#if NEXAR_GEO2_AHEAD
+  // Group prefetch: the CTAs of the first tile column pull the frames of the group that will be processed about one wave
+  // from now (NEXAR_GEO2_AHEAD groups further on) from DRAM into L2 with the bulk-copy engine, one slice of a frame per
+  // CTA row and thread: by the time that group's tiles gather from it, every load is an L2 hit.
+  if (blockIdx.x == 0 && threadIdx.x < NF) {
+    const int gz = bz - NEXAR_GEO2_AHEAD * (NEXAR_GEO2_REVERSE ? 1 : -1);
+    if (gz >= 0 && gz < (int)gridDim.z) {
+      const int c2 = gz / ngroup, t2 = (gz - c2 * ngroup) * NF + (int)threadIdx.x;
+      if (t2 < A.T) {
+        const char* base = (const char*)(A.inter + (int64_t)(c2 * A.T + t2) * FPX);
+        const int per = ((FPX * 8 / (int)gridDim.y) + 15) & ~15, off = (int)blockIdx.y * per;
+        const int n = min(per, FPX * 8 - off);
+        if (n > 0) l2_prefetch_bulk(base + off, (unsigned)n);
+      }
+    }
+  }
 #endif
   const int clip = bz / ngroup;
   const int t0 = (bz - clip * ngroup) * NF;
